@@ -1,0 +1,182 @@
+/*
+ * opesci_b200.h -- C ABI of the B200-native opesci-fd time-stepping library
+ *
+ * Drop-in boundary.  The reference JIT-compiles one shared object per model
+ * and loads it with ctypes (reference: opesci/grid.py:35-42); that object exports exactly
+ *
+ *     int opesci_execute    (OpesciGrid *grid, OpesciProfiling *profiling);
+ *     int opesci_convergence(OpesciGrid *grid, OpesciConvergence *conv);
+ *     int opesci_free       (OpesciGrid *grid);
+ *
+ * (reference: opesci/templates/regular3d_tmpl.py:44-48, 106-118; struct layouts
+ * regular3d_tmpl.py:19-23, 41-42 and opesci/regulargrid.py:435-443, 636-642, 349-354).
+ * The same three symbols with the same struct layouts are exported here.
+ *
+ * In the reference every model parameter (dims, dt, ntsteps, the stencil coefficients as
+ * decimal float literals, the analytic solution) is baked into the generated source
+ * (opesci/regulargrid.py:391-406).  A prebuilt library needs them at run time, so ONE
+ * additive call carries them: opesci_b200_configure().  The parameter block holds exactly
+ * the values the generator would have printed, already rounded the way the printer rounds
+ * them (opesci/codeprinter.py:30,46-63: 15 significant digits, then an `F` float literal).
+ *
+ * Plain C, plain pointers and sizes only.  No torch types.
+ */
+#ifndef OPESCI_B200_H
+#define OPESCI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPESCI_MAX_M 6            /* so/2 for so <= 12 */
+#define OPESCI_MAX_FIELDS 9
+#define OPESCI_MAX_TABLES 12
+#define OPESCI_MAX_PROG 48
+#define OPESCI_PROG_STACK 12
+
+/* ---- reference structs (field order = grid.fields: U,V,W,Txx,Tyy,Tzz,Txy,Tyz,Txz;
+ *      opesci/staggeredgrid.py:69-71, tests/eigenwave3d.py:64-67) ---------------------- */
+/* The reference declares `real_t *` members; pointer size is the same for float/double, so
+ * one layout serves both precisions (the ctypes side always uses POINTER(c_float),
+ * opesci/grid.py:106).  A RegularGrid model has ONE member (its user-named field). */
+typedef struct OpesciGrid {
+    void *field[OPESCI_MAX_FIELDS];
+} OpesciGrid;
+
+/* `real_t <field>_l2` per field (opesci/regulargrid.py:636-642).  Written as float or double
+ * according to the configured precision, packed in field order. */
+typedef union OpesciConvergence {
+    float f32[OPESCI_MAX_FIELDS];
+    double f64[OPESCI_MAX_FIELDS];
+} OpesciConvergence;
+
+/* opesci/regulargrid.py:349-354 (no PAPI events: GPU build has no PAPI) */
+typedef struct OpesciProfiling {
+    float g_rtime;   /* seconds spent in the time loop (CUDA events) */
+    float g_ptime;   /* seconds of opesci_execute wall time */
+    float g_mflops;  /* reference op count (48*so flop/point/step, regulargrid.py:293-327) / g_rtime */
+} OpesciProfiling;
+
+/* ---- analytic-solution programs ---------------------------------------------------------
+ * The reference prints the user's sympy solution into the init loops and the L2 loops
+ * (opesci/staggeredgrid.py:612-659, 892-945; opesci/regulargrid.py:498-528, 650-700) and libm
+ * evaluates it per cell in double.  Here the host evaluates every maximal sub-expression that
+ * depends on ONE spatial index (e.g. sin(M_PI*y)) into a 1-D table with the same libm, and
+ * the remaining + - * tree runs per cell on the device in IEEE double -- same operations,
+ * same order, same bits. */
+enum {
+    OPESCI_OP_TABLE = 1, /* push table[arg][index along its axis] */
+    OPESCI_OP_CONST = 2, /* push value */
+    OPESCI_OP_ADD = 3,
+    OPESCI_OP_SUB = 4,
+    OPESCI_OP_MUL = 5,
+    OPESCI_OP_NEG = 6,
+    OPESCI_OP_DIV = 7,
+    OPESCI_OP_FIELD = 8  /* push (double)F[x][y][z]: only in `final_` programs */
+};
+
+typedef struct OpesciSolInstr {
+    int32_t op;
+    int32_t arg;
+    double value;
+} OpesciSolInstr;
+
+typedef struct OpesciSolProgram {
+    int32_t n_instr;
+    int32_t n_tables;
+    int32_t table_axis[OPESCI_MAX_TABLES];   /* 0,1,2 = generator axes x,y,z (dim1,dim2,dim3) */
+    const double *table[OPESCI_MAX_TABLES];  /* HOST pointers, dim[axis] entries each */
+    OpesciSolInstr instr[OPESCI_MAX_PROG];
+} OpesciSolProgram;
+
+typedef struct OpesciFieldSpec {
+    int32_t lo[3], hi[3];        /* init loop ranges [lo,hi) per axis (staggeredgrid.py:632-640, regulargrid.py:508-511) */
+    int32_t l2_lo[3], l2_hi[3];  /* L2 loop ranges (staggeredgrid.py:918-926, regulargrid.py:676-681) */
+    OpesciSolProgram init;       /* solution at the field's first time (0 or dt/2) */
+    OpesciSolProgram final_;     /* the whole printed residual `F - sol(t_last)` (uses OPESCI_OP_FIELD);
+                                  * L2 = sqrt(volume_literal * sum residual^2) */
+} OpesciFieldSpec;
+
+enum { OPESCI_KIND_STAGGERED_ELASTIC = 1, OPESCI_KIND_REGULAR_ACOUSTIC = 2 };
+
+/* flags */
+enum {
+    OPESCI_ARITH_REFERENCE = 0,      /* term order + separate mul/add exactly as emitted: bit-exact */
+    OPESCI_ARITH_FAST = 1,           /* factored c_k*(a-b), FMA contraction allowed */
+    OPESCI_ARITH_MASK = 0x3,
+    OPESCI_HOST_MIRROR_FULL = 0 << 4,   /* grid->field[] = host arrays, all time levels (reference ABI) */
+    OPESCI_HOST_MIRROR_NONE = 1 << 4,   /* grid->field[] = DEVICE pointers; nothing copied back */
+    OPESCI_HOST_MIRROR_MASK = 0x30,
+    OPESCI_NO_CUDA_GRAPH = 1 << 8,
+    OPESCI_FORCE_UNFUSED = 1 << 9       /* two-pass stress / velocity kernels (diagnostic) */
+};
+
+typedef struct OpesciB200Params {
+    uint32_t struct_size;        /* sizeof(OpesciB200Params): layout check */
+    int32_t kind;
+    int32_t so;                  /* spatial order 2..12; margin m = so/2 (regulargrid.py:128) */
+    int32_t is_double;           /* real_t = double (switch `double`, regulargrid.py:27-28) */
+    int32_t dim[3];              /* dim1..3 = grid_size + 1 + 2m (regulargrid.py:152) */
+    int32_t ntsteps;
+    int32_t nfields;             /* 9 (staggered) or 1 (regular) */
+    int32_t nlevels;             /* time levels tp: 2 (staggered), 3 (regular, regulargrid.py:118-120) */
+    int32_t converge;            /* switch `converge` */
+    int32_t free_surface;        /* 1: Levander (so==4), 2: Robertsson (so!=4), 0: none (staggeredgrid.py:223-226) */
+    int32_t flags;
+    int32_t reserved_i[3];
+    double dt;
+    double dx[3];
+    double volume_literal;       /* dx1*dx2*dx3 as printed (float literal) for the L2 scale */
+
+    /* ---- staggered elastic, homogeneous medium: every literal of the emitted kernels ------
+     * c_* = c_k * dt/dx_d * {lambda+2mu | lambda | mu | beta}, k = 1..m, magnitude AND sign of
+     * the +offset half of the window; the -offset half uses the negated value. */
+    float c_stress_normal[3][3][OPESCI_MAX_M];   /* [T_aa: a][axis d][k-1]   staggeredgrid.py:728-737 */
+    float c_stress_shear[3][2][OPESCI_MAX_M];    /* [Txy,Tyz,Txz][term][k-1]; term0 = d_b V_a, term1 = d_a V_b */
+    float c_velocity[3][3][OPESCI_MAX_M];        /* [V_a][axis d][k-1]       staggeredgrid.py:739-748 */
+    /* Levander free surface, so == 4 only (fields.py:208-242, 313-353) */
+    float lev_stress[3][3][3][2];  /* [face axis d][T_ee: e][derivative axis f][k-1], e != d, f != d */
+    float lev_vnormal[3][3];       /* [d][e]: r*dx_d/dx_e  (fields.py:220-224), e != d */
+    float lev_vtang[3][3];         /* [d][e]: dx_d/dx_e    (fields.py:226-230), e != d */
+
+    /* ---- regular acoustic (regulargrid.py:592-619, 530-564) ------------------------------ */
+    float ac_coef[3][OPESCI_MAX_M];   /* [axis][k-1]: weight of u[t1][i+-k]; 0 if the axis is absent */
+    float ac_centre;                  /* weight of u[t1][i] */
+    float ac_init_coef[3][OPESCI_MAX_M];
+    float ac_init_centre;
+    double ac_init_const;             /* the `1.0F*v*dt` term, evaluated in real_t by the host */
+
+    OpesciFieldSpec fields[OPESCI_MAX_FIELDS];
+} OpesciB200Params;
+
+/* ---- entry points ---------------------------------------------------------------------- */
+/* Replaces: the constants baked by opesci/regulargrid.py:391-406 into every generated file.
+ * Must be called before opesci_execute; copies everything it needs (tables included). */
+int opesci_b200_configure(const OpesciB200Params *params);
+
+/* Replaces generated opesci_execute (templates/regular3d_tmpl.py:44-59, staggered3d_tmpl.py:9-58):
+ * allocates the fields (zero-filled), runs init + init BCs + ntsteps steps, stores
+ * the base pointers into *grid.  Returns 0, or non-zero with opesci_b200_last_error() set. */
+int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling);
+
+/* Replaces generated opesci_convergence (regular3d_tmpl.py:106-112; staggeredgrid.py:892-945). */
+int opesci_convergence(OpesciGrid *grid, OpesciConvergence *conv);
+
+/* Replaces generated opesci_free (regular3d_tmpl.py:114-118; regulargrid.py:621-634). */
+int opesci_free(OpesciGrid *grid);
+
+/* Additive helpers (no reference counterpart) */
+const char *opesci_b200_last_error(void);
+/* L2 sums in double: out[f] = sqrt(volume * sum (F - sol)^2), double accumulation */
+int opesci_b200_convergence_f64(OpesciGrid *grid, double *out_l2);
+/* timing of the last opesci_execute: seconds in the time loop (device events) and point updates */
+int opesci_b200_last_timing(double *loop_seconds, double *points_per_step, int64_t *kernel_launches);
+/* 1 if this library was built with the CUDA kernels (0 for the CPU oracle build) */
+int opesci_b200_is_cuda(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPESCI_B200_H */

@@ -1,0 +1,130 @@
+"""ctypes mirror of include/opesci_b200.h and the loader of the CUDA library.
+
+Replaces the reference's "compile the generated file, then cdll.LoadLibrary it" step
+(reference: opesci/grid.py:35-42, 99-103; opesci/compilation.py:26-48).  The product path
+loads opesci_fd_b200/csrc/libopesci_b200.so (hand-written sm_100a CUDA behind a C ABI) and
+fails loudly when it is missing -- there is no CPU fallback.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, Structure, Union, c_char_p, c_double, c_float, c_int32, c_int64,
+                    c_uint32, c_void_p)
+
+OPESCI_MAX_M = 6
+OPESCI_MAX_FIELDS = 9
+OPESCI_MAX_TABLES = 12
+OPESCI_MAX_PROG = 48
+
+OP_TABLE, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_DIV, OP_FIELD = 1, 2, 3, 4, 5, 6, 7, 8
+
+KIND_STAGGERED_ELASTIC = 1
+KIND_REGULAR_ACOUSTIC = 2
+
+ARITH_REFERENCE = 0
+ARITH_FAST = 1
+HOST_MIRROR_FULL = 0 << 4
+HOST_MIRROR_NONE = 1 << 4
+NO_CUDA_GRAPH = 1 << 8
+FORCE_UNFUSED = 1 << 9
+
+FS_NONE, FS_LEVANDER, FS_ROBERTSSON = 0, 1, 2
+
+
+class OpesciGrid(Structure):
+    _fields_ = [("field", c_void_p * OPESCI_MAX_FIELDS)]
+
+
+class OpesciConvergence(Union):
+    _fields_ = [("f32", c_float * OPESCI_MAX_FIELDS), ("f64", c_double * OPESCI_MAX_FIELDS)]
+
+
+class OpesciProfiling(Structure):
+    _fields_ = [("g_rtime", c_float), ("g_ptime", c_float), ("g_mflops", c_float)]
+
+
+class OpesciSolInstr(Structure):
+    _fields_ = [("op", c_int32), ("arg", c_int32), ("value", c_double)]
+
+
+class OpesciSolProgram(Structure):
+    _fields_ = [("n_instr", c_int32), ("n_tables", c_int32),
+                ("table_axis", c_int32 * OPESCI_MAX_TABLES),
+                ("table", POINTER(c_double) * OPESCI_MAX_TABLES),
+                ("instr", OpesciSolInstr * OPESCI_MAX_PROG)]
+
+
+class OpesciFieldSpec(Structure):
+    _fields_ = [("lo", c_int32 * 3), ("hi", c_int32 * 3),
+                ("l2_lo", c_int32 * 3), ("l2_hi", c_int32 * 3),
+                ("init", OpesciSolProgram), ("final_", OpesciSolProgram)]
+
+
+class OpesciB200Params(Structure):
+    _fields_ = [
+        ("struct_size", c_uint32), ("kind", c_int32), ("so", c_int32), ("is_double", c_int32),
+        ("dim", c_int32 * 3), ("ntsteps", c_int32), ("nfields", c_int32), ("nlevels", c_int32),
+        ("converge", c_int32), ("free_surface", c_int32), ("flags", c_int32),
+        ("reserved_i", c_int32 * 3),
+        ("dt", c_double), ("dx", c_double * 3), ("volume_literal", c_double),
+        ("c_stress_normal", ((c_float * OPESCI_MAX_M) * 3) * 3),
+        ("c_stress_shear", ((c_float * OPESCI_MAX_M) * 2) * 3),
+        ("c_velocity", ((c_float * OPESCI_MAX_M) * 3) * 3),
+        ("lev_stress", (((c_float * 2) * 3) * 3) * 3),
+        ("lev_vnormal", (c_float * 3) * 3),
+        ("lev_vtang", (c_float * 3) * 3),
+        ("ac_coef", (c_float * OPESCI_MAX_M) * 3),
+        ("ac_centre", c_float),
+        ("ac_init_coef", (c_float * OPESCI_MAX_M) * 3),
+        ("ac_init_centre", c_float),
+        ("ac_init_const", c_double),
+        ("fields", OpesciFieldSpec * OPESCI_MAX_FIELDS),
+    ]
+
+
+EXPORTED_SYMBOLS = [
+    "opesci_b200_configure", "opesci_execute", "opesci_convergence", "opesci_free",
+    "opesci_b200_last_error", "opesci_b200_convergence_f64", "opesci_b200_last_timing",
+    "opesci_b200_is_cuda",
+]
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CUDA_LIBRARY = os.path.join(_PKG_DIR, "csrc", "libopesci_b200.so")
+
+
+def bind(lib):
+    """Declare argument / result types on a loaded library exporting include/opesci_b200.h."""
+    lib.opesci_b200_configure.argtypes = [POINTER(OpesciB200Params)]
+    lib.opesci_b200_configure.restype = ctypes.c_int
+    lib.opesci_execute.argtypes = [POINTER(OpesciGrid), POINTER(OpesciProfiling)]
+    lib.opesci_execute.restype = ctypes.c_int
+    lib.opesci_convergence.argtypes = [POINTER(OpesciGrid), POINTER(OpesciConvergence)]
+    lib.opesci_convergence.restype = ctypes.c_int
+    lib.opesci_free.argtypes = [POINTER(OpesciGrid)]
+    lib.opesci_free.restype = ctypes.c_int
+    lib.opesci_b200_last_error.argtypes = []
+    lib.opesci_b200_last_error.restype = c_char_p
+    lib.opesci_b200_convergence_f64.argtypes = [POINTER(OpesciGrid), POINTER(c_double)]
+    lib.opesci_b200_convergence_f64.restype = ctypes.c_int
+    lib.opesci_b200_last_timing.argtypes = [POINTER(c_double), POINTER(c_double), POINTER(c_int64)]
+    lib.opesci_b200_last_timing.restype = ctypes.c_int
+    lib.opesci_b200_is_cuda.argtypes = []
+    lib.opesci_b200_is_cuda.restype = ctypes.c_int
+    return lib
+
+
+def load_library(path=None):
+    """Load the CUDA library (or an explicitly given ABI-compatible one).
+
+    Mirrors Grid._load_library (reference: opesci/grid.py:35-42): a load failure raises.
+    """
+    libname = path or CUDA_LIBRARY
+    if not os.path.exists(libname):
+        raise Exception("Failed to load %s: file not found (build it with "
+                        "`python -c 'import __graft_entry__ as g; g.build()'`); "
+                        "there is no CPU fallback" % libname)
+    try:
+        lib = ctypes.CDLL(libname, mode=ctypes.RTLD_GLOBAL)
+    except OSError as e:
+        print("Library load error: ", e)
+        raise Exception("Failed to load %s" % libname)
+    return bind(lib)

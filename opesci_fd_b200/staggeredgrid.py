@@ -1,0 +1,267 @@
+"""StaggeredGrid: velocity-stress formulation of elastic waves on a staggered grid.
+
+Mirrors the reference interface opesci/staggeredgrid.py:15-945 (constructor keywords,
+`set_stress_fields`, `set_velocity_fields`, `calc_derivatives`, `solve_fd`,
+`set_free_surface_boundary`, `set_media_params`, `get_time_step_limit`, the AI reports).
+Where the reference derives update expressions symbolically and prints them as C++
+(staggeredgrid.py:135-170, 612-945), this class reads the PDE coefficients off the equations
+and lowers the model to the literal tables the generated code would have contained
+(`build_params`), for the fixed-function sm_100a kernels:
+
+  c_k * dt/dx_d * {lambda+2mu | lambda | mu | beta}     interior updates   (staggeredgrid.py:728-748)
+  Levander / Robertsson free-surface parameters          ghost-cell loops   (staggeredgrid.py:750-864,
+                                                                             fields.py:192-261, 294-381)
+  analytic-solution programs + loop ranges               init / L2          (staggeredgrid.py:612-659, 892-945)
+"""
+from fractions import Fraction
+
+from sympy import Symbol
+
+from . import abi, cexpr
+from .codeprinter import ccode, literal
+from .derivative import DDerivative
+from .fields import SField, VField
+from .regulargrid import RegularGrid, _frac
+from .util import staggered_first_weights
+
+__all__ = ['StaggeredGrid']
+
+# canonical slots (struct order of the reference driver, tests/eigenwave3d.py:54-67)
+_NORMAL = [(1, 1), (2, 2), (3, 3)]
+_SHEAR = [(1, 2), (2, 3), (1, 3)]
+
+
+class StaggeredGrid(RegularGrid):
+    _switches = ['omp', 'ivdep', 'simd', 'double', 'expand', 'eval_const',
+                 'output_vts', 'converge', 'profiling', 'pluto', 'fission']
+    _papi_events = []
+
+    def __init__(self, stress_fields=None, velocity_fields=None, converge=False, **kwargs):
+        self.sfields = []
+        self.vfields = []
+        self._free_surface = set()
+        super(StaggeredGrid, self).__init__(**kwargs)
+        self.converge = converge
+        if stress_fields:
+            self.set_stress_fields(stress_fields)
+        if velocity_fields:
+            self.set_velocity_fields(velocity_fields)
+
+    @property
+    def fields(self):
+        """velocity fields first, then stress fields (reference: staggeredgrid.py:69-71)"""
+        return self.vfields + self.sfields
+
+    @property
+    def io(self):
+        return self.read or self.output_vts
+
+    def set_alignment(self, alignment):
+        self.alignment = alignment
+
+    def get_time_step_limit(self):
+        """reference: staggeredgrid.py:85-102"""
+        if self.read:
+            return 'physical parameters to be read from file, please compile and run the executable'
+        l = self.defined_variable['lambda'].value
+        m = self.defined_variable['mu'].value
+        r = self.defined_variable['rho'].value
+        Vp = ((l + 2 * m) / r) ** 0.5
+        h = min([sp.value for sp in self.spacing])
+        if self.order[1] == 2:
+            return h / Vp / (3 ** 0.5)
+        elif self.order[1] == 4:
+            return 0.495 * h / Vp
+        else:
+            return 'not implemented yet'
+
+    def set_stress_fields(self, sfields):
+        """reference: staggeredgrid.py:104-114"""
+        num = self.dimension + self.dimension * (self.dimension - 1) // 2
+        if not len(sfields) == num:
+            raise Exception('wrong number of stress fields: ' + str(num) + ' fields required.')
+        self.sfields = sfields
+        self.set_field_spacing()
+
+    def set_velocity_fields(self, vfields):
+        """reference: staggeredgrid.py:116-126"""
+        num = self.dimension
+        if not len(vfields) == num:
+            raise Exception('wrong number of velocity fields: ' + str(num) + ' fields required.')
+        self.vfields = vfields
+        self.set_field_spacing()
+
+    def calc_derivatives(self):
+        """reference: staggeredgrid.py:128-133"""
+        for field in self.sfields + self.vfields:
+            field.populate_derivatives(max_order=1)
+
+    def set_media_params(self, read=False, rho=1.0, vp=1.0, vs=0.5, rho_file='', vp_file='', vs_file=''):
+        """reference: staggeredgrid.py:234-282"""
+        self.read = read
+        if self.read:
+            raise NotImplementedError("heterogeneous media (read=True): the reference's own output for "
+                                      "this mode is NaN (SURVEY.md 0.8); not lowered in this round")
+        self.set_variable('rho', rho, 'float', True)
+        self.set_variable('beta', 1.0 / rho, 'float', True)
+        self.set_variable('lambda', rho * (vp ** 2 - 2 * vs ** 2), 'float', True)
+        self.set_variable('mu', rho * (vs ** 2), 'float', True)
+
+    # ------------------------------------------------------------------ PDE analysis
+    def _slot_fields(self):
+        """Check that the nine fields are the canonical U,V,W,Txx,Tyy,Tzz,Txy,Tyz,Txz."""
+        if self.dimension != 3:
+            raise NotImplementedError("B200 path: 3-D models only")
+        vel = [f for f in self.vfields if isinstance(f, VField)]
+        if [f.direction for f in vel] != [1, 2, 3]:
+            raise NotImplementedError("velocity_fields must be given in direction order 1,2,3")
+        dirs = [tuple(f.direction) for f in self.sfields if isinstance(f, SField)]
+        if dirs != _NORMAL + _SHEAR:
+            raise NotImplementedError("stress_fields must be Txx,Tyy,Tzz,Txy,Tyz,Txz (directions %s)"
+                                      % (_NORMAL + _SHEAR,))
+        normal = {d[0]: f for d, f in zip(dirs[:3], self.sfields[:3])}
+        shear = {d: f for d, f in zip(dirs[3:], self.sfields[3:])}
+        return {f.direction: f for f in vel}, normal, shear
+
+    def solve_fd(self, equations):
+        """reference: staggeredgrid.py:135-170.  Reads every PDE as
+        `dF/dt = sum coef * dG/dx_d` and checks it has the velocity-stress structure the
+        fixed-function kernels implement; keeps the coefficient EXPRESSIONS (evaluated at
+        lowering time with the current media constants, like the reference's eval_const)."""
+        if not len(self.fields) == len(equations):
+            raise KeyError("Number of equations must be the same as number of fields.")
+        self.eq = list(equations)
+        vel, normal, shear = self._slot_fields()
+
+        def stress_of(a, d):
+            return normal[a] if a == d else shear[tuple(sorted((a, d)))]
+
+        self.pde = {}
+        for field, eq in zip(self.fields, self.eq):
+            lhs = eq.lhs
+            if not (isinstance(lhs, DDerivative) and lhs.field is field and lhs.axis == 0 and lhs.order == 1):
+                raise NotImplementedError("equation %s: left side must be d%s/dt" % (eq, field.label))
+            field.set_dt(eq.rhs)
+            coefs = self._linear_coefficients(eq)
+            table = {}
+            for d, c in coefs.items():
+                if d.order != 1 or d.axis == 0:
+                    raise NotImplementedError("unsupported derivative %s" % d)
+                table[(d.field, d.axis)] = c
+            # expected sparsity
+            if isinstance(field, VField):
+                a = field.direction
+                want = {(stress_of(a, d), d) for d in (1, 2, 3)}
+            elif field.direction[0] == field.direction[1]:
+                want = {(vel[d], d) for d in (1, 2, 3)}
+            else:
+                a, b = field.direction
+                want = {(vel[a], b), (vel[b], a)}
+            if set(table) != want:
+                raise NotImplementedError(
+                    "equation for %s is not of velocity-stress form (B200 kernels are fixed-function; "
+                    "general PDEs are SURVEY.md 8f item 4)" % field.label)
+            self.pde[field] = table
+
+    def set_free_surface_boundary(self, dimension, side):
+        """reference: staggeredgrid.py:214-232.  Levander for so == 4, Robertsson otherwise."""
+        self._free_surface.add((dimension, side))
+
+    # ------------------------------------------------------------------ AI reports
+    def get_stress_kernel_ai(self):
+        """expanded form: 15*so ADD = MUL, 9 loads, 6 stores (regulargrid.py:293-327)"""
+        return self._ai(15 * self.order[1], 9, 6)
+
+    def get_velocity_kernel_ai(self):
+        return self._ai(9 * self.order[1], 9, 3)
+
+    def _ai(self, ops, load, store):
+        word = 8 if self.double else 4
+        ai = float(2 * ops) / (load + store) / word
+        return (ai, ai, ops, ops, load, store)
+
+    def get_overall_kernel_ai(self):
+        """Interior kernels only, with the reference's ghost-cell adjustment
+        (staggeredgrid.py:481-510); the boundary-loop weights (O(1/N)) are not included."""
+        v, s = self.get_velocity_kernel_ai(), self.get_stress_kernel_ai()
+        overall = (v[0] + s[0]) / 2.0
+        adj = 1.0
+        for d in self.dim[1:]:
+            adj *= 1 - float(self.margin.value) / d.value
+        return overall * adj, overall * adj
+
+    # ------------------------------------------------------------------ lowering
+    def build_params(self):
+        if not getattr(self, 'pde', None):
+            raise RuntimeError("solve_fd() must be called before the model can be lowered")
+        if self._free_surface != {(d, s) for d in (1, 2, 3) for s in (0, 1)}:
+            raise NotImplementedError("all six faces must be free surfaces "
+                                      "(set_free_surface_boundary(dimension=1..3, side=0..1))")
+        if len(set(self.order[1:])) != 1:
+            raise NotImplementedError("equal spatial order on all axes required")
+        if self.order[0] != 2:
+            raise NotImplementedError("time order %d" % self.order[0])
+        keep = []
+        so = self.order[1]
+        m = so // 2
+        vel, normal, shear = self._slot_fields()
+        p = self._common_params(abi.KIND_STAGGERED_ELASTIC, 9, 2)
+        p.free_surface = abi.FS_LEVANDER if so == 4 else abi.FS_ROBERTSSON
+        ck = staggered_first_weights(m)
+        dt = _frac(self.dt.value)
+        dx = [None] + [_frac(sp.value) for sp in self.spacing]
+
+        def val(expr):
+            return _frac(self._value(expr))
+
+        def fill(dst, coef, d):
+            for k in range(m):
+                dst[k] = literal(float(ck[k] * dt / dx[d] * coef))
+
+        # interior updates
+        M = {}
+        for a in (1, 2, 3):
+            for d in (1, 2, 3):
+                M[(a, d)] = val(self.pde[normal[a]][(vel[d], d)])
+                fill(p.c_stress_normal[a - 1][d - 1], M[(a, d)], d)
+                g = normal[a] if a == d else shear[tuple(sorted((a, d)))]
+                fill(p.c_velocity[a - 1][d - 1], val(self.pde[vel[a]][(g, d)]), d)
+        for s, (a, b) in enumerate(_SHEAR):
+            fill(p.c_stress_shear[s][0], val(self.pde[shear[(a, b)]][(vel[a], b)]), b)
+            fill(p.c_stress_shear[s][1], val(self.pde[shear[(a, b)]][(vel[b], a)]), a)
+        # Levander free surface (so == 4): eliminate d_d V_d with T_dd' = 0 (fields.py:313-353)
+        # and build the ghost velocities from 2nd-order differences (fields.py:208-242)
+        if so == 4:
+            for d in (1, 2, 3):
+                for e in (1, 2, 3):
+                    if e == d:
+                        continue
+                    for f in (1, 2, 3):
+                        if f == d:
+                            continue
+                        coef = M[(e, f)] - M[(e, d)] * M[(d, f)] / M[(d, d)]
+                        fill(p.lev_stress[d - 1][e - 1][f - 1], coef, f)
+                    ratio = float(dx[d] / dx[e])
+                    p.lev_vnormal[d - 1][e - 1] = literal(float(M[(d, e)] / M[(d, d)] * dx[d] / dx[e]))
+                    sh = shear[tuple(sorted((d, e)))]
+                    c_tang = val(self.pde[sh][(vel[d], e)]) / val(self.pde[sh][(vel[e], d)])
+                    p.lev_vtang[d - 1][e - 1] = literal(float(c_tang) * ratio)
+        # init / L2: loops stop one short on staggered axes; coordinates are half-shifted there
+        # (staggeredgrid.py:632-641, 918-927); first time dt/2 for velocities (staggeredgrid.py:647)
+        loop = [Symbol('_' + x.name) for x in self.index]
+        ti = self.ntsteps.value % 2
+        dims = [self.dim[d].value for d in range(3)]
+        for k, field in enumerate(self.fields):
+            stag = [bool(field.staggered[d + 1]) for d in range(3)]
+            lo = [m] * 3
+            hi = [dims[d] - m - (1 if stag[d] else 0) for d in range(3)]
+            coords = self._coordinates(stag)
+            t0 = self.dt.value / 2 if field.staggered[0] else 0
+            tn = self.dt.value * self.ntsteps.value if not field.staggered[0] \
+                else self.dt.value * self.ntsteps.value + self.dt.value / 2.0
+            ivars = self._solution_variables(coords)
+            fvars = self._solution_variables(coords)
+            fvars.field('__F__', cexpr.DOUBLE if self.double else cexpr.FLOAT)
+            self._field_spec(p, k, field, lo, hi, lo, hi, ccode(field.sol.subs(self.t, t0)), ivars,
+                             self._residual_text(field, ti, tn, loop), fvars, keep)
+        return p, keep

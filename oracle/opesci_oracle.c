@@ -1,0 +1,405 @@
+/*
+ * opesci_oracle.c -- CPU restatement of opesci-fd's generated time-stepping code.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity oracle: it may be built, loaded or
+ * executed only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.  It is
+ * never on the product path (the product is opesci_fd_b200/csrc, CUDA only).
+ *
+ * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this restatement
+ * BIT-FOR-BIT against the reference's own generated OpenMP C++ (oracle/_ref, built by
+ * oracle/refgen/make_ref.py from /root/reference) for so = 2..12, fp32 and fp64, staggered
+ * and regular grids, and against the committed golden fixtures in tests/golden/.
+ *
+ * It exports the same C ABI as the CUDA library (include/opesci_b200.h) so that one ctypes
+ * binding drives both.  What is restated (reference file:line):
+ *   - stress / velocity interior updates          opesci/staggeredgrid.py:728-748,
+ *                                                  opesci/regulargrid.py:566-590, 601-619
+ *   - stress free-surface / ghost loops            opesci/staggeredgrid.py:750-813, opesci/fields.py:294-381
+ *   - velocity free-surface / ghost loops          opesci/staggeredgrid.py:815-864, opesci/fields.py:192-261
+ *   - time-level rotation                          opesci/regulargrid.py:408-433
+ *   - initialisation + initial BC pass             opesci/staggeredgrid.py:612-659, 866-879
+ *   - regular-grid update and second initialisation opesci/regulargrid.py:498-564, 592-619
+ *   - L2 convergence                               opesci/staggeredgrid.py:892-945, opesci/regulargrid.py:650-700
+ *   - allocate / store / free                      opesci/regulargrid.py:445-453, 474-496, 621-634
+ *
+ * Arithmetic contract (what makes bit-exactness possible): the generator prints every
+ * update as a flat left-to-right sum of `literal*G[...]` products (expand=True,
+ * eval_const=True, opesci/regulargrid.py:329-342) with float literals
+ * (opesci/codeprinter.py:30,63); gcc without -ffast-math evaluates that as one rounded
+ * multiply and one rounded add per term.  Build this file with -ffp-contract=off.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/opesci_b200.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* ------------------------------------------------------------------ model ---- */
+enum { TERM_MUL = 0, TERM_PLUS = 1, TERM_MINUS = 2 };
+
+typedef struct {
+    int kind;      /* TERM_MUL: acc += coef*G ; TERM_PLUS/MINUS: acc +/-= G (exact self terms) */
+    int field;
+    int level;     /* index into the current {t0,t1,t2} triple */
+    long off;      /* element offset inside one time level */
+    float coef;    /* signed float literal */
+} Term;
+
+#define MAX_TERMS 96
+typedef struct {
+    int out, out_level, nterm;
+    Term term[MAX_TERMS];
+} Equation;
+
+typedef struct {
+    OpesciB200Params p;
+    int m;
+    long s[3];              /* strides of axes x,y,z inside one level */
+    size_t level_elems;
+    Equation stress[6], velocity[3], acoustic, acoustic_init;
+    Equation lev_stress_eq[3][3];    /* [face axis d][normal stress e] */
+    Equation lev_vel_eq[3][3][2];    /* [face axis d][velocity a][side] */
+    double *tables;         /* private copy of every 1-D table */
+    int configured;
+} Model;
+
+static Model g_model;
+static char g_err[512] = "";
+static double g_loop_seconds = 0.0;
+
+static int fail(const char *msg)
+{
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return 1;
+}
+
+const char *opesci_b200_last_error(void) { return g_err; }
+int opesci_b200_is_cuda(void) { return 0; }
+
+/* field ids in struct order (opesci/staggeredgrid.py:69-71) */
+enum { F_U = 0, F_V, F_W, F_TXX, F_TYY, F_TZZ, F_TXY, F_TYZ, F_TXZ };
+static const int NORMAL_OF_AXIS[3] = {F_TXX, F_TYY, F_TZZ};
+static const int VEL_OF_AXIS[3] = {F_U, F_V, F_W};
+/* shear field for an axis pair */
+static int shear_of(int a, int b)
+{
+    if (a > b) { int t = a; a = b; b = t; }
+    if (a == 0 && b == 1) return F_TXY;
+    if (a == 1 && b == 2) return F_TYZ;
+    return F_TXZ;
+}
+
+static void push(Equation *eq, int kind, int field, int level, long off, float coef)
+{
+    Term *t = &eq->term[eq->nterm++];
+    t->kind = kind; t->field = field; t->level = level; t->off = off; t->coef = coef;
+}
+
+/* First-derivative window of G along one axis, in the order the printer emits it
+ * (verified on the generated files): positive offsets ascending, negative
+ * offsets by ascending magnitude, offset 0 last.
+ *   forward  (F staggered along the axis, G not; opesci/fields.py:127-128):
+ *            sum_k c_k (G[i+k] - G[i-k+1])    offsets -m+1 .. m
+ *   backward (G staggered along the axis, F not; opesci/fields.py:131-132):
+ *            sum_k c_k (G[i+k-1] - G[i-k])    offsets -m .. m-1
+ * c[k-1] carries c_k*dt/dx*material, sign included. */
+static void push_window(Equation *eq, int field, int level, long stride, int m, const float *c, int forward)
+{
+    if (forward) {
+        for (int o = 1; o <= m; ++o) push(eq, TERM_MUL, field, level, o * stride, c[o - 1]);
+        for (int o = 1; o <= m - 1; ++o) push(eq, TERM_MUL, field, level, -o * stride, -c[o]);
+        push(eq, TERM_MUL, field, level, 0, -c[0]);
+    } else {
+        for (int o = 1; o <= m - 1; ++o) push(eq, TERM_MUL, field, level, o * stride, c[o]);
+        for (int o = 1; o <= m; ++o) push(eq, TERM_MUL, field, level, -o * stride, -c[o - 1]);
+        push(eq, TERM_MUL, field, level, 0, c[0]);
+    }
+}
+
+/* opesci/staggeredgrid.py:728-748 via regulargrid.py:601-619; term order = alphabetical by
+ * field name (Txx<Txy<Txz<Tyy<Tyz<Tzz<U<V<W), so the self term leads the stress sums and
+ * closes the velocity sums. */
+static void build_staggered(Model *M)
+{
+    const OpesciB200Params *p = &M->p;
+    const int m = M->m;
+    /* normal stresses: T_aa[t1] = T_aa[t0] + sum_d coef(a,d) * D_d V_d  (backward windows) */
+    for (int a = 0; a < 3; ++a) {
+        Equation *eq = &M->stress[a];
+        eq->out = NORMAL_OF_AXIS[a]; eq->out_level = 1; eq->nterm = 0;
+        push(eq, TERM_PLUS, eq->out, 0, 0, 1.0f);
+        for (int d = 0; d < 3; ++d)
+            push_window(eq, VEL_OF_AXIS[d], 0, M->s[d], m, p->c_stress_normal[a][d], 0);
+    }
+    /* shear stresses, emitted order Txy, Tyz, Txz: T_ab += mu*(D_b V_a + D_a V_b), forward windows */
+    static const int PAIR[3][2] = {{0, 1}, {1, 2}, {0, 2}};
+    for (int s = 0; s < 3; ++s) {
+        const int a = PAIR[s][0], b = PAIR[s][1];
+        Equation *eq = &M->stress[3 + s];
+        eq->out = shear_of(a, b); eq->out_level = 1; eq->nterm = 0;
+        push(eq, TERM_PLUS, eq->out, 0, 0, 1.0f);
+        push_window(eq, VEL_OF_AXIS[a], 0, M->s[b], m, p->c_stress_shear[s][0], 1);
+        push_window(eq, VEL_OF_AXIS[b], 0, M->s[a], m, p->c_stress_shear[s][1], 1);
+    }
+    /* velocities: V_a[t1] = sum_d coef(a,d) * D_d T_ad[t1] + V_a[t0] */
+    for (int a = 0; a < 3; ++a) {
+        Equation *eq = &M->velocity[a];
+        eq->out = VEL_OF_AXIS[a]; eq->out_level = 1; eq->nterm = 0;
+        for (int d = 0; d < 3; ++d) {
+            const int g = (d == a) ? NORMAL_OF_AXIS[a] : shear_of(a, d);
+            push_window(eq, g, 1, M->s[d], m, p->c_velocity[a][d], d == a);
+        }
+        push(eq, TERM_PLUS, eq->out, 0, 0, 1.0f);
+    }
+}
+
+
+/* Levander free surface, so == 4 (m == 2) only.
+ * Stress (opesci/fields.py:313-353): on face d, T_ee (e != d) is recomputed from level t0:
+ *   T_ee[t1] = 1.0F*T_ee[t0] + sum_{f != d} lev_stress[d][e][f][.] * D_f V_f   (backward windows)
+ * Velocity (opesci/fields.py:208-242), all operands at level t1:
+ *   normal     V_d[n]   = V_d[n+-1] +/- sum_{e != d} a_e (V_e[e:0] - V_e[e:-1])   at plane b
+ *   tangential V_e[n]   = 2 V_e[b] - V_e[b+-1] +/- g (D+_e V_d[n'] - D+_e V_d[b])
+ * Term order = alphabetical by field name, then lexicographic by index with "+1 before 0" on
+ * loop indices and the nearer plane first (verified against the generated files). */
+static void build_levander(Model *M)
+{
+    const OpesciB200Params *p = &M->p;
+    const int m = M->m;
+    for (int d = 0; d < 3; ++d)
+        for (int e = 0; e < 3; ++e) {
+            Equation *eq = &M->lev_stress_eq[d][e];
+            eq->out = NORMAL_OF_AXIS[e]; eq->out_level = 1; eq->nterm = 0;
+            if (e == d) continue;
+            push(eq, TERM_PLUS, eq->out, 0, 0, 1.0f);
+            for (int f = 0; f < 3; ++f)
+                if (f != d) push_window(eq, VEL_OF_AXIS[f], 0, M->s[f], m, p->lev_stress[d][e][f], 0);
+        }
+    for (int d = 0; d < 3; ++d)
+        for (int a = 0; a < 3; ++a)
+            for (int side = 0; side < 2; ++side) {
+                Equation *eq = &M->lev_vel_eq[d][a][side];
+                const long sd = M->s[d];
+                eq->out = VEL_OF_AXIS[a]; eq->out_level = 0; eq->nterm = 0;
+                if (a == d) {
+                    /* target plane n: low n = m-1 (reads plane m), high n = dim-m-1 (reads itself
+                     * for the tangential differences and plane n-1 for the self term) */
+                    const float sgn = side == 0 ? 1.0f : -1.0f;
+                    const long plane = side == 0 ? sd : 0;       /* offset of the plane the differences live on */
+                    const long selfoff = side == 0 ? sd : -sd;
+                    for (int g = 0; g < 3; ++g) {
+                        if (g == d) {
+                            push(eq, TERM_PLUS, VEL_OF_AXIS[d], 0, selfoff, 1.0f);
+                        } else {
+                            const float c = p->lev_vnormal[d][g];
+                            push(eq, TERM_MUL, VEL_OF_AXIS[g], 0, plane - M->s[g], -sgn * c);
+                            push(eq, TERM_MUL, VEL_OF_AXIS[g], 0, plane, sgn * c);
+                        }
+                    }
+                } else {
+                    /* tangential field V_a on face d; target plane n: low n = m-1 (b = n+1),
+                     * high n = dim-m (b' = n-1) */
+                    const int e = a;
+                    const float g = p->lev_vtang[d][e];
+                    const float sgn = side == 0 ? 1.0f : -1.0f;
+                    const long se = M->s[e];
+                    /* planes of V_d used: low: n (=b-1) and n+1 (=b); high: n-1 (=b') and n-2 */
+                    const long pl0 = side == 0 ? 0 : -sd, pl1 = side == 0 ? sd : -2 * sd;
+                    /* self planes: low 2V[b]-V[b+1]; high 2V[b']-V[b'-1] */
+                    const long sf0 = side == 0 ? sd : -sd, sf1 = side == 0 ? 2 * sd : -2 * sd;
+                    if (d < e) {
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl0 + se, sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl0, -sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl1 + se, -sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl1, sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[e], 0, sf0, 2.0f);
+                        push(eq, TERM_MINUS, VEL_OF_AXIS[e], 0, sf1, 1.0f);
+                    } else {
+                        push(eq, TERM_MUL, VEL_OF_AXIS[e], 0, sf0, 2.0f);
+                        push(eq, TERM_MINUS, VEL_OF_AXIS[e], 0, sf1, 1.0f);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, se + pl0, sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, se + pl1, -sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl0, -sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl1, sgn * g);
+                    }
+                }
+            }
+}
+
+/* opesci/regulargrid.py:592-619 (update) and 530-564 (second initialisation).  Central
+ * second-derivative windows; emitted order per axis: +1..+m, -1..-m; centre last. */
+static void build_regular(Model *M)
+{
+    const OpesciB200Params *p = &M->p;
+    const int m = M->m;
+    Equation *eq = &M->acoustic;
+    eq->out = 0; eq->out_level = 2; eq->nterm = 0;
+    push(eq, TERM_MINUS, 0, 0, 0, 1.0f);
+    for (int d = 0; d < 3; ++d) {
+        int present = 0;
+        for (int k = 0; k < m; ++k) present |= (p->ac_coef[d][k] != 0.0f);
+        if (!present) continue;
+        for (int o = 1; o <= m; ++o) push(eq, TERM_MUL, 0, 1, o * M->s[d], p->ac_coef[d][o - 1]);
+        for (int o = 1; o <= m; ++o) push(eq, TERM_MUL, 0, 1, -o * M->s[d], p->ac_coef[d][o - 1]);
+    }
+    push(eq, TERM_MUL, 0, 1, 0, p->ac_centre);
+    /* level t1 := `1.0F*v*dt` + halved stencil of level t0 (the constant is added first) */
+    eq = &M->acoustic_init;
+    eq->out = 0; eq->out_level = 1; eq->nterm = 0;
+    for (int d = 0; d < 3; ++d) {
+        int present = 0;
+        for (int k = 0; k < m; ++k) present |= (p->ac_init_coef[d][k] != 0.0f);
+        if (!present) continue;
+        for (int o = 1; o <= m; ++o) push(eq, TERM_MUL, 0, 0, o * M->s[d], p->ac_init_coef[d][o - 1]);
+        for (int o = 1; o <= m; ++o) push(eq, TERM_MUL, 0, 0, -o * M->s[d], p->ac_init_coef[d][o - 1]);
+    }
+    push(eq, TERM_MUL, 0, 0, 0, p->ac_init_centre);
+}
+
+int opesci_b200_configure(const OpesciB200Params *params)
+{
+    Model *M = &g_model;
+    if (!params || params->struct_size != sizeof(OpesciB200Params))
+        return fail("opesci_b200_configure: struct_size mismatch");
+    if (params->so < 2 || params->so > 12 || (params->so & 1))
+        return fail("opesci_b200_configure: so must be even, 2..12");
+    free(M->tables);
+    memset(M, 0, sizeof *M);
+    M->p = *params;
+    M->m = params->so / 2;
+    M->s[0] = (long)params->dim[1] * params->dim[2];
+    M->s[1] = params->dim[2];
+    M->s[2] = 1;
+    M->level_elems = (size_t)params->dim[0] * params->dim[1] * params->dim[2];
+    /* deep-copy tables */
+    size_t total = 0;
+    for (int f = 0; f < params->nfields; ++f)
+        for (int w = 0; w < 2; ++w) {
+            const OpesciSolProgram *pr = w ? &params->fields[f].final_ : &params->fields[f].init;
+            for (int t = 0; t < pr->n_tables; ++t) total += (size_t)params->dim[pr->table_axis[t]];
+        }
+    M->tables = (double *)malloc((total ? total : 1) * sizeof(double));
+    size_t pos = 0;
+    for (int f = 0; f < params->nfields; ++f)
+        for (int w = 0; w < 2; ++w) {
+            OpesciSolProgram *pr = w ? &M->p.fields[f].final_ : &M->p.fields[f].init;
+            for (int t = 0; t < pr->n_tables; ++t) {
+                size_t n = (size_t)params->dim[pr->table_axis[t]];
+                memcpy(M->tables + pos, pr->table[t], n * sizeof(double));
+                pr->table[t] = M->tables + pos;
+                pos += n;
+            }
+        }
+    if (params->kind == OPESCI_KIND_STAGGERED_ELASTIC) {
+        if (params->nfields != 9 || params->nlevels != 2) return fail("staggered: need 9 fields, 2 levels");
+        build_staggered(M);
+        if (params->free_surface == 1) {
+            if (params->so != 4) return fail("Levander free surface needs so == 4");
+            build_levander(M);
+        }
+    } else if (params->kind == OPESCI_KIND_REGULAR_ACOUSTIC) {
+        if (params->nfields != 1 || params->nlevels != 3) return fail("regular: need 1 field, 3 levels");
+        build_regular(M);
+    } else {
+        return fail("opesci_b200_configure: unknown kind");
+    }
+    M->configured = 1;
+    g_err[0] = 0;
+    return 0;
+}
+
+static double run_program(const OpesciSolProgram *pr, int x, int y, int z, double fieldval)
+{
+    double st[OPESCI_PROG_STACK];
+    int sp = 0;
+    const int idx[3] = {x, y, z};
+    for (int i = 0; i < pr->n_instr; ++i) {
+        const OpesciSolInstr *in = &pr->instr[i];
+        switch (in->op) {
+        case OPESCI_OP_TABLE: st[sp++] = pr->table[in->arg][idx[pr->table_axis[in->arg]]]; break;
+        case OPESCI_OP_CONST: st[sp++] = in->value; break;
+        case OPESCI_OP_FIELD: st[sp++] = fieldval; break;
+        case OPESCI_OP_ADD: sp--; st[sp - 1] = st[sp - 1] + st[sp]; break;
+        case OPESCI_OP_SUB: sp--; st[sp - 1] = st[sp - 1] - st[sp]; break;
+        case OPESCI_OP_MUL: sp--; st[sp - 1] = st[sp - 1] * st[sp]; break;
+        case OPESCI_OP_DIV: sp--; st[sp - 1] = st[sp - 1] / st[sp]; break;
+        case OPESCI_OP_NEG: st[sp - 1] = -st[sp - 1]; break;
+        default: break;
+        }
+    }
+    return sp > 0 ? st[sp - 1] : 0.0;
+}
+
+#include <time.h>
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+/* ------------------------------------------------- precision-generic section ---- */
+#define REAL float
+#define SFX(n) n##_f32
+#include "opesci_oracle_loops.inc"
+#undef REAL
+#undef SFX
+#define REAL double
+#define SFX(n) n##_f64
+#include "opesci_oracle_loops.inc"
+#undef REAL
+#undef SFX
+
+/* ------------------------------------------------------------------ C ABI ---- */
+int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
+{
+    Model *M = &g_model;
+    if (!M->configured) return fail("opesci_execute: opesci_b200_configure was not called");
+    double t0 = now_s();
+    int rc = M->p.is_double ? execute_f64(M, grid) : execute_f32(M, grid);
+    if (profiling) {
+        profiling->g_rtime = (float)g_loop_seconds;
+        profiling->g_ptime = (float)(now_s() - t0);
+        profiling->g_mflops = 0.0f;
+    }
+    return rc;
+}
+
+int opesci_convergence(OpesciGrid *grid, OpesciConvergence *conv)
+{
+    Model *M = &g_model;
+    if (!M->configured) return fail("opesci_convergence: not configured");
+    return M->p.is_double ? convergence_f64(M, grid, conv, NULL) : convergence_f32(M, grid, conv, NULL);
+}
+
+int opesci_b200_convergence_f64(OpesciGrid *grid, double *out)
+{
+    Model *M = &g_model;
+    if (!M->configured) return fail("opesci_b200_convergence_f64: not configured");
+    return M->p.is_double ? convergence_f64(M, grid, NULL, out) : convergence_f32(M, grid, NULL, out);
+}
+
+int opesci_free(OpesciGrid *grid)
+{
+    /* opesci/regulargrid.py:621-634 */
+    for (int f = 0; f < g_model.p.nfields; ++f) {
+        free(grid->field[f]);
+        grid->field[f] = NULL;
+    }
+    return 0;
+}
+
+int opesci_b200_last_timing(double *loop_seconds, double *points_per_step, int64_t *kernel_launches)
+{
+    const Model *M = &g_model;
+    if (loop_seconds) *loop_seconds = g_loop_seconds;
+    if (points_per_step)
+        *points_per_step = (double)(M->p.dim[0] - 2 * M->m) * (M->p.dim[1] - 2 * M->m) * (M->p.dim[2] - 2 * M->m);
+    if (kernel_launches) *kernel_launches = 0;
+    return 0;
+}
