@@ -1,0 +1,397 @@
+// kernels.cuh -- sm_100a kernels of the opesci-fd time-stepping hot path.
+//
+// What each kernel replaces in the reference's generated OpenMP C++:
+//   stress_interior<SO,T,ARITH>    stress loop      opesci/staggeredgrid.py:728-737 -> regulargrid.py:566-619
+//   velocity_interior<SO,T,ARITH>  velocity loop    opesci/staggeredgrid.py:739-748
+//   face_mirror<T>, face_equation<T>  the 30+18 (so=4) / 18+18 ghost-cell loops
+//                                  opesci/staggeredgrid.py:750-864, opesci/fields.py:192-261, 294-381
+//   acoustic_interior<SO,T,ARITH>  regular-grid update + second initialisation  regulargrid.py:530-564, 592-619
+//   init_field<T>, l2_partial<T>   analytic initialisation / L2 test  staggeredgrid.py:612-659, 892-945
+//
+// Arithmetic modes (include/opesci_b200.h):
+//   ARITH_REFERENCE  every emitted term is one rounded multiply (__fmul_rn/__dmul_rn) and one
+//                    rounded add, in the printer's term order -> bit-identical to the generated
+//                    code built without FMA contraction (g++ -O3, x86-64 baseline).
+//   ARITH_FAST       factored sum_k c_k*(a-b) with FMA contraction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/opesci_b200.h"
+
+namespace opesci {
+
+enum { F_U = 0, F_V, F_W, F_TXX, F_TYY, F_TZZ, F_TXY, F_TYZ, F_TXZ };
+
+struct FieldPtrs {
+    void *f[OPESCI_MAX_FIELDS];   // base of [nlevels][dim1][dim2][dim3]
+};
+
+struct GridGeom {
+    int dim[3];
+    int m;
+    long long s[3];       // element strides of axes x,y,z inside one level
+    long long level;      // elements per time level
+};
+
+// literal tables (float, exactly as the generated source holds them)
+struct StaggeredCoefs {
+    float sn[3][3][OPESCI_MAX_M];
+    float ss[3][2][OPESCI_MAX_M];
+    float v[3][3][OPESCI_MAX_M];
+};
+struct AcousticCoefs {
+    float c[3][OPESCI_MAX_M];
+    float centre;
+    int present[3];
+};
+
+// ------------------------------------------------------------------ rounded primitives
+template <typename T> __device__ __forceinline__ T mul_rn(T a, T b);
+template <> __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <typename T> __device__ __forceinline__ T add_rn(T a, T b);
+template <> __device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
+
+// acc (+)= c*g with separate rounding; `first` starts the sum with the product itself
+template <typename T>
+__device__ __forceinline__ void term(T &acc, bool &first, float c, T g)
+{
+    const T prod = mul_rn<T>((T)c, g);
+    acc = first ? prod : add_rn<T>(acc, prod);
+    first = false;
+}
+
+// One first-derivative window in the printer's order: +offsets ascending,
+// -offsets by ascending magnitude, offset 0 last.
+//   FWD  (target staggered along the axis):  sum_k c_k (g[k] - g[-k+1]),  offsets -M+1..M
+//   !FWD (operand staggered along the axis): sum_k c_k (g[k-1] - g[-k]), offsets -M..M-1
+// g points at offset 0; stride in elements.
+template <int M, typename T, bool FWD>
+__device__ __forceinline__ void window_ref(T &acc, bool &first, const T *__restrict__ g, long long stride,
+                                           const float *c)
+{
+    if (FWD) {
+#pragma unroll
+        for (int o = 1; o <= M; ++o) term<T>(acc, first, c[o - 1], g[o * stride]);
+#pragma unroll
+        for (int o = 1; o <= M - 1; ++o) term<T>(acc, first, -c[o], g[-o * stride]);
+        term<T>(acc, first, -c[0], g[0]);
+    } else {
+#pragma unroll
+        for (int o = 1; o <= M - 1; ++o) term<T>(acc, first, c[o], g[o * stride]);
+#pragma unroll
+        for (int o = 1; o <= M; ++o) term<T>(acc, first, -c[o - 1], g[-o * stride]);
+        term<T>(acc, first, c[0], g[0]);
+    }
+}
+
+// factored derivative (FAST mode): sum_k c_k (g[+] - g[-])
+template <int M, typename T, bool FWD>
+__device__ __forceinline__ T window_fast(const T *__restrict__ g, long long stride, const float *c)
+{
+    T d = 0;
+#pragma unroll
+    for (int k = 1; k <= M; ++k) {
+        const T a = FWD ? g[k * stride] : g[(k - 1) * stride];
+        const T b = FWD ? g[(-k + 1) * stride] : g[-k * stride];
+        d += (T)c[k - 1] * (a - b);
+    }
+    return d;
+}
+
+// ------------------------------------------------------------------ interior kernels (v1)
+// One thread per grid point, neighbours through L1/L2.  x,y,z in [m, dim-m) for every field
+// regardless of staggering (regulargrid.py:573-578).
+template <int SO, typename T, int ARITH>
+__global__ void __launch_bounds__(256)
+stress_interior(FieldPtrs F, GridGeom G, StaggeredCoefs C, int t0, int t1)
+{
+    constexpr int M = SO / 2;
+    const int z = M + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = M + blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = M + blockIdx.z;
+    if (z >= G.dim[2] - M || y >= G.dim[1] - M) return;
+    const long long p = (long long)x * G.s[0] + (long long)y * G.s[1] + z;
+    const long long r = (long long)t0 * G.level + p, w = (long long)t1 * G.level + p;
+    const T *U = (const T *)F.f[F_U] + r, *V = (const T *)F.f[F_V] + r, *W = (const T *)F.f[F_W] + r;
+    const long long sx = G.s[0], sy = G.s[1], sz = 1;
+    // normal stresses: self, then D_x U, D_y V, D_z W (backward windows)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        T *Tn = (T *)F.f[F_TXX + a];
+        if (ARITH == OPESCI_ARITH_REFERENCE) {
+            T acc = Tn[r];
+            bool first = false;
+            window_ref<M, T, false>(acc, first, U, sx, C.sn[a][0]);
+            window_ref<M, T, false>(acc, first, V, sy, C.sn[a][1]);
+            window_ref<M, T, false>(acc, first, W, sz, C.sn[a][2]);
+            Tn[w] = acc;
+        } else {
+            Tn[w] = Tn[r] + (window_fast<M, T, false>(U, sx, C.sn[a][0]) + window_fast<M, T, false>(V, sy, C.sn[a][1]) +
+                             window_fast<M, T, false>(W, sz, C.sn[a][2]));
+        }
+    }
+    // shear stresses Txy, Tyz, Txz: self, then D_b V_a, D_a V_b (forward windows)
+    {
+        const T *A[3] = {U, V, U}, *B[3] = {V, W, W};
+        const long long sa[3] = {sy, sz, sz}, sb[3] = {sx, sy, sx};
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            T *Ts = (T *)F.f[F_TXY + s];
+            if (ARITH == OPESCI_ARITH_REFERENCE) {
+                T acc = Ts[r];
+                bool first = false;
+                window_ref<M, T, true>(acc, first, A[s], sa[s], C.ss[s][0]);
+                window_ref<M, T, true>(acc, first, B[s], sb[s], C.ss[s][1]);
+                Ts[w] = acc;
+            } else {
+                Ts[w] = Ts[r] + (window_fast<M, T, true>(A[s], sa[s], C.ss[s][0]) +
+                                 window_fast<M, T, true>(B[s], sb[s], C.ss[s][1]));
+            }
+        }
+    }
+}
+
+template <int SO, typename T, int ARITH>
+__global__ void __launch_bounds__(256)
+velocity_interior(FieldPtrs F, GridGeom G, StaggeredCoefs C, int t0, int t1)
+{
+    constexpr int M = SO / 2;
+    const int z = M + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = M + blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = M + blockIdx.z;
+    if (z >= G.dim[2] - M || y >= G.dim[1] - M) return;
+    const long long p = (long long)x * G.s[0] + (long long)y * G.s[1] + z;
+    const long long r = (long long)t0 * G.level + p, w = (long long)t1 * G.level + p;
+    const long long st[3] = {G.s[0], G.s[1], 1};
+    // V_a[t1] = sum_d c(a,d) D_d T_ad[t1] + V_a[t0]; operand order x,y,z = alphabetical
+    const int opnd[3][3] = {{F_TXX, F_TXY, F_TXZ}, {F_TXY, F_TYY, F_TYZ}, {F_TXZ, F_TYZ, F_TZZ}};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        T *Va = (T *)F.f[F_U + a];
+        if (ARITH == OPESCI_ARITH_REFERENCE) {
+            T acc = 0;
+            bool first = true;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const T *g = (const T *)F.f[opnd[a][d]] + w;
+                if (d == a) window_ref<M, T, true>(acc, first, g, st[d], C.v[a][d]);
+                else window_ref<M, T, false>(acc, first, g, st[d], C.v[a][d]);
+            }
+            Va[w] = add_rn<T>(acc, Va[r]);
+        } else {
+            T acc = 0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const T *g = (const T *)F.f[opnd[a][d]] + w;
+                acc += (d == a) ? window_fast<M, T, true>(g, st[d], C.v[a][d])
+                                : window_fast<M, T, false>(g, st[d], C.v[a][d]);
+            }
+            Va[w] = Va[r] + acc;
+        }
+    }
+}
+
+// u[tw] = [constant +] [-u[tprev]] + sum_axes sum_k c_k (u[tr][+k], then u[tr][-k]) + centre*u[tr]
+// (regulargrid.py:592-619; second initialisation regulargrid.py:530-564 with HAS_PREV = false)
+template <int SO, typename T, int ARITH, bool HAS_PREV>
+__global__ void __launch_bounds__(256)
+acoustic_interior(FieldPtrs F, GridGeom G, AcousticCoefs C, int tprev, int tr, int tw, T constant)
+{
+    constexpr int M = SO / 2;
+    const int z = M + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = M + blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = M + blockIdx.z;
+    if (z >= G.dim[2] - M || y >= G.dim[1] - M) return;
+    const long long p = (long long)x * G.s[0] + (long long)y * G.s[1] + z;
+    T *u = (T *)F.f[0];
+    const T *g = u + (long long)tr * G.level + p;
+    const long long st[3] = {G.s[0], G.s[1], 1};
+    T acc;
+    bool first;
+    if (HAS_PREV) { acc = -u[(long long)tprev * G.level + p]; first = false; }
+    else { acc = constant; first = false; }
+    if (ARITH == OPESCI_ARITH_REFERENCE) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (!C.present[d]) continue;
+#pragma unroll
+            for (int o = 1; o <= M; ++o) term<T>(acc, first, C.c[d][o - 1], g[o * st[d]]);
+#pragma unroll
+            for (int o = 1; o <= M; ++o) term<T>(acc, first, C.c[d][o - 1], g[-o * st[d]]);
+        }
+        term<T>(acc, first, C.centre, g[0]);
+    } else {
+        T sum = (T)C.centre * g[0];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (!C.present[d]) continue;
+#pragma unroll
+            for (int o = 1; o <= M; ++o) sum += (T)C.c[d][o - 1] * (g[o * st[d]] + g[-o * st[d]]);
+        }
+        acc += sum;
+    }
+    u[(long long)tw * G.level + p] = acc;
+}
+
+// ------------------------------------------------------------------ face (ghost-cell) kernels
+enum { TERM_MUL = 0, TERM_PLUS = 1, TERM_MINUS = 2 };
+struct DevTerm {
+    int kind, field, level;
+    float coef;
+    long long off;
+};
+#define OPESCI_MAX_FACE_TERMS 12
+struct DevEq {
+    int out, out_level, nterm, pad;
+    DevTerm term[OPESCI_MAX_FACE_TERMS];
+};
+
+// One reference loop `for e1 in [lo,hi1) for e2 in [lo,hi2): out[plane n] = sum terms`
+// (Levander loops, always in reference arithmetic: they are O(N^2)).
+template <typename T>
+__global__ void face_equation(FieldPtrs F, GridGeom G, DevEq eq, int lv0, int lv1, int d, int n, int lo, int hi1,
+                              int hi2)
+{
+    const int e1 = (d == 0) ? 1 : 0, e2 = (d == 2) ? 1 : 2;
+    const int j = lo + blockIdx.x * blockDim.x + threadIdx.x;   // along e2 (contiguous unless d == 2)
+    const int i = lo + blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= hi1 || j >= hi2) return;
+    const long long p = (long long)i * G.s[e1] + (long long)j * G.s[e2] + (long long)n * G.s[d];
+    const long long lv[2] = {(long long)lv0 * G.level, (long long)lv1 * G.level};
+    T acc = 0;
+    bool first = true;
+    for (int k = 0; k < eq.nterm; ++k) {
+        const DevTerm t = eq.term[k];
+        const T g = ((const T *)F.f[t.field])[lv[t.level] + p + t.off];
+        T v;
+        if (t.kind == TERM_MUL) v = mul_rn<T>((T)t.coef, g);
+        else if (t.kind == TERM_PLUS) v = g;
+        else v = -g;
+        acc = first ? v : add_rn<T>(acc, v);
+        first = false;
+    }
+    ((T *)F.f[eq.out])[lv[eq.out_level] + p] = acc;
+}
+
+// One reference loop made of plane assignments  field[dst_k] = 0 | -field[src_k]  along axis d.
+struct MirrorOps {
+    int count;
+    int dst[OPESCI_MAX_M], src[OPESCI_MAX_M];   // plane indices along d; src < 0: assign 0
+};
+template <typename T>
+__global__ void face_mirror(T *__restrict__ A /* level base */, GridGeom G, MirrorOps ops, int d, int lo, int hi1,
+                            int hi2)
+{
+    const int e1 = (d == 0) ? 1 : 0, e2 = (d == 2) ? 1 : 2;
+    const int j = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = lo + blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= hi1 || j >= hi2) return;
+    const long long q = (long long)i * G.s[e1] + (long long)j * G.s[e2];
+    for (int k = 0; k < ops.count; ++k) {
+        const T v = ops.src[k] < 0 ? (T)0 : -A[q + (long long)ops.src[k] * G.s[d]];
+        A[q + (long long)ops.dst[k] * G.s[d]] = v;
+    }
+}
+
+// ------------------------------------------------------------------ analytic programs
+struct DevProgram {
+    int n_instr, n_tables;
+    int table_axis[OPESCI_MAX_TABLES];
+    const double *table[OPESCI_MAX_TABLES];   // device pointers
+    OpesciSolInstr instr[OPESCI_MAX_PROG];
+};
+
+__device__ __forceinline__ double run_program(const DevProgram &pr, int x, int y, int z, double fieldval)
+{
+    double st[OPESCI_PROG_STACK];
+    int sp = 0;
+    for (int i = 0; i < pr.n_instr; ++i) {
+        const int op = pr.instr[i].op;
+        if (op == OPESCI_OP_TABLE) {
+            const int a = pr.instr[i].arg;
+            const int ax = pr.table_axis[a];
+            st[sp++] = pr.table[a][ax == 0 ? x : (ax == 1 ? y : z)];
+        } else if (op == OPESCI_OP_CONST) {
+            st[sp++] = pr.instr[i].value;
+        } else if (op == OPESCI_OP_FIELD) {
+            st[sp++] = fieldval;
+        } else if (op == OPESCI_OP_NEG) {
+            st[sp - 1] = -st[sp - 1];
+        } else {
+            --sp;
+            const double a = st[sp - 1], b = st[sp];
+            st[sp - 1] = op == OPESCI_OP_ADD ? __dadd_rn(a, b)
+                         : op == OPESCI_OP_SUB ? __dsub_rn(a, b)
+                         : op == OPESCI_OP_MUL ? __dmul_rn(a, b) : __ddiv_rn(a, b);
+        }
+    }
+    return sp > 0 ? st[sp - 1] : 0.0;
+}
+
+struct Range3 { int lo[3], hi[3]; };
+
+template <typename T>
+__global__ void init_field(T *__restrict__ A /* level 0 */, GridGeom G, Range3 R, const DevProgram *__restrict__ prog)
+{
+    __shared__ DevProgram pr;
+    for (int i = threadIdx.x + threadIdx.y * blockDim.x; i < (int)(sizeof(DevProgram) / 4); i += blockDim.x * blockDim.y)
+        ((int *)&pr)[i] = ((const int *)prog)[i];
+    __syncthreads();
+    const int z = R.lo[2] + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = R.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = R.lo[0] + blockIdx.z;
+    if (z >= R.hi[2] || y >= R.hi[1]) return;
+    A[(long long)x * G.s[0] + (long long)y * G.s[1] + z] = (T)run_program(pr, x, y, z, 0.0);
+}
+
+// per-block partial sums of residual^2 in double; partial[blockIdx linear]
+template <typename T>
+__global__ void l2_partial(const T *__restrict__ A /* level ti */, GridGeom G, Range3 R,
+                           const DevProgram *__restrict__ prog, double *__restrict__ partial)
+{
+    __shared__ DevProgram pr;
+    __shared__ double red[32];
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    for (int i = tid; i < (int)(sizeof(DevProgram) / 4); i += blockDim.x * blockDim.y)
+        ((int *)&pr)[i] = ((const int *)prog)[i];
+    __syncthreads();
+    const int z = R.lo[2] + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = R.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = R.lo[0] + blockIdx.z;
+    double v = 0.0;
+    if (z < R.hi[2] && y < R.hi[1]) {
+        const double e = run_program(pr, x, y, z, (double)A[(long long)x * G.s[0] + (long long)y * G.s[1] + z]);
+        v = e * e;
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+        const int nw = (blockDim.x * blockDim.y + 31) / 32;
+        v = tid < nw ? red[tid] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (tid == 0)
+            partial[(size_t)blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z)] = v;
+    }
+}
+
+// deterministic final sum of the partials (fixed order, one block)
+__global__ void l2_final(const double *__restrict__ partial, size_t n, double *__restrict__ out)
+{
+    __shared__ double red[32];
+    double v = 0.0;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) v += partial[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = threadIdx.x < (blockDim.x + 31) / 32 ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) *out = v;
+    }
+}
+
+}  // namespace opesci

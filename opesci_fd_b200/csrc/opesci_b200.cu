@@ -1,0 +1,725 @@
+// opesci_b200.cu -- C ABI (include/opesci_b200.h) and host orchestration of the CUDA kernels.
+//
+// Replaces the reference's generated `opesci_execute / opesci_convergence / opesci_free`
+// (opesci/templates/regular3d_tmpl.py:44-59, 106-118; staggered3d_tmpl.py:9-58).  Per call:
+//   opesci_execute: allocate + zero the fields on the device, analytic
+//   initialisation, initial BC pass, `ntsteps` leapfrog steps replayed from a CUDA graph
+//   (stress interior -> stress ghost loops -> velocity interior -> velocity ghost loops, the
+//   order is a contract: staggered3d_tmpl.py:40-58), then (HOST_MIRROR_FULL) copy every time
+//   level back into host arrays whose base pointers are stored into *grid, like the
+//   reference does (regulargrid.py:445-453).
+// There is no CPU fallback: every entry point fails loudly without a CUDA device.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace opesci;
+
+namespace {
+
+char g_err[1024] = "";
+int fail(const char *fmt, const char *a = "", const char *b = "")
+{
+    snprintf(g_err, sizeof g_err, fmt, a, b);
+    return 1;
+}
+#define CUDA_OK(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) return fail("CUDA error: %s at %s", cudaGetErrorString(e_), #call); \
+    } while (0)
+
+struct Launch;   // one recorded kernel launch of a time step
+
+struct Model {
+    OpesciB200Params p;
+    bool configured = false;
+    int m = 0;
+    GridGeom G;
+    StaggeredCoefs sc;
+    AcousticCoefs ac, ac_init;
+    DevEq lev_stress_eq[3][3];
+    DevEq lev_vel_eq[3][3][2];
+    std::vector<double> tables;                  // host copy of every table
+    std::vector<size_t> table_off[OPESCI_MAX_FIELDS][2];
+};
+Model g_model;
+
+// device-resident state of one executed model, keyed by the pointer stored in grid->field[0]
+struct Run {
+    Model M;
+    void *dev[OPESCI_MAX_FIELDS] = {};
+    void *host[OPESCI_MAX_FIELDS] = {};
+    bool host_pinned = false;
+    double *d_tables = nullptr;
+    DevProgram *d_prog = nullptr;   // [nfields][2]
+    size_t bytes_per_field = 0;
+};
+std::map<void *, Run *> g_runs;
+std::mutex g_mu;
+
+double g_loop_seconds = 0.0;
+long long g_launches = 0;
+
+// ------------------------------------------------------------------ model construction
+void push(DevEq &eq, int kind, int field, int level, long long off, float coef)
+{
+    DevTerm &t = eq.term[eq.nterm++];
+    t.kind = kind; t.field = field; t.level = level; t.off = off; t.coef = coef;
+}
+const int NORMAL_OF_AXIS[3] = {F_TXX, F_TYY, F_TZZ};
+const int VEL_OF_AXIS[3] = {F_U, F_V, F_W};
+
+// backward window, m == 2, printer order +1, -1, -2, 0 (opesci/fields.py:313-353)
+void push_window_bwd2(DevEq &eq, int field, int level, long long stride, const float *c)
+{
+    push(eq, TERM_MUL, field, level, stride, c[1]);
+    push(eq, TERM_MUL, field, level, -stride, -c[0]);
+    push(eq, TERM_MUL, field, level, -2 * stride, -c[1]);
+    push(eq, TERM_MUL, field, level, 0, c[0]);
+}
+
+// Levander free-surface loops (so == 4): term order as emitted by the reference printer,
+// alphabetical by field name then lexicographic by index (verified bit-for-bit through the
+// oracle, tests/test_oracle_golden.py).
+void build_levander(Model &M)
+{
+    const OpesciB200Params &p = M.p;
+    const long long *s = M.G.s;
+    for (int d = 0; d < 3; ++d)
+        for (int e = 0; e < 3; ++e) {
+            DevEq &eq = M.lev_stress_eq[d][e];
+            eq.out = NORMAL_OF_AXIS[e]; eq.out_level = 1; eq.nterm = 0;
+            if (e == d) continue;
+            push(eq, TERM_PLUS, eq.out, 0, 0, 1.0f);   // `1.0F*T[t0]` is exact
+            for (int f = 0; f < 3; ++f)
+                if (f != d) push_window_bwd2(eq, VEL_OF_AXIS[f], 0, s[f], p.lev_stress[d][e][f]);
+        }
+    for (int d = 0; d < 3; ++d)
+        for (int a = 0; a < 3; ++a)
+            for (int side = 0; side < 2; ++side) {
+                DevEq &eq = M.lev_vel_eq[d][a][side];
+                const long long sd = s[d];
+                const float sgn = side == 0 ? 1.0f : -1.0f;
+                eq.out = VEL_OF_AXIS[a]; eq.out_level = 0; eq.nterm = 0;
+                if (a == d) {
+                    // normal component: V_d[n] = V_d[n +- 1] +- sum_e a_e (V_e[e:0] - V_e[e:-1]) on the face plane
+                    const long long plane = side == 0 ? sd : 0, selfoff = side == 0 ? sd : -sd;
+                    for (int g = 0; g < 3; ++g) {
+                        if (g == d) {
+                            push(eq, TERM_PLUS, VEL_OF_AXIS[d], 0, selfoff, 1.0f);
+                        } else {
+                            const float c = p.lev_vnormal[d][g];
+                            push(eq, TERM_MUL, VEL_OF_AXIS[g], 0, plane - s[g], -sgn * c);
+                            push(eq, TERM_MUL, VEL_OF_AXIS[g], 0, plane, sgn * c);
+                        }
+                    }
+                } else {
+                    // tangential component V_e on face d
+                    const int e = a;
+                    const float g = p.lev_vtang[d][e];
+                    const long long se = s[e];
+                    const long long pl0 = side == 0 ? 0 : -sd, pl1 = side == 0 ? sd : -2 * sd;
+                    const long long sf0 = side == 0 ? sd : -sd, sf1 = side == 0 ? 2 * sd : -2 * sd;
+                    if (d < e) {
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl0 + se, sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl0, -sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl1 + se, -sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl1, sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[e], 0, sf0, 2.0f);
+                        push(eq, TERM_MINUS, VEL_OF_AXIS[e], 0, sf1, 1.0f);
+                    } else {
+                        push(eq, TERM_MUL, VEL_OF_AXIS[e], 0, sf0, 2.0f);
+                        push(eq, TERM_MINUS, VEL_OF_AXIS[e], 0, sf1, 1.0f);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, se + pl0, sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, se + pl1, -sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl0, -sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl1, sgn * g);
+                    }
+                }
+            }
+}
+
+// ------------------------------------------------------------------ launch helpers
+struct Stepper {
+    const Run &R;
+    cudaStream_t st;
+    long long launches = 0;
+    cudaError_t err = cudaSuccess;
+    Stepper(const Run &r, cudaStream_t s) : R(r), st(s) {}
+
+    FieldPtrs ptrs() const
+    {
+        FieldPtrs F;
+        for (int f = 0; f < OPESCI_MAX_FIELDS; ++f) F.f[f] = R.dev[f];
+        return F;
+    }
+    void check()
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+        ++launches;
+    }
+    dim3 interior_grid(dim3 blk) const
+    {
+        const Model &M = R.M;
+        const int nz = M.G.dim[2] - 2 * M.m, ny = M.G.dim[1] - 2 * M.m, nx = M.G.dim[0] - 2 * M.m;
+        return dim3((nz + blk.x - 1) / blk.x, (ny + blk.y - 1) / blk.y, nx);
+    }
+
+    template <int SO, typename T, int ARITH> void stress(int t0, int t1)
+    {
+        dim3 blk(64, 4);
+        stress_interior<SO, T, ARITH><<<interior_grid(blk), blk, 0, st>>>(ptrs(), R.M.G, R.M.sc, t0, t1);
+        check();
+    }
+    template <int SO, typename T, int ARITH> void velocity(int t0, int t1)
+    {
+        dim3 blk(64, 4);
+        velocity_interior<SO, T, ARITH><<<interior_grid(blk), blk, 0, st>>>(ptrs(), R.M.G, R.M.sc, t0, t1);
+        check();
+    }
+    template <int SO, typename T, int ARITH> void acoustic(int tprev, int tr, int tw, bool init)
+    {
+        dim3 blk(64, 4);
+        if (init)
+            acoustic_interior<SO, T, ARITH, false><<<interior_grid(blk), blk, 0, st>>>(
+                ptrs(), R.M.G, R.M.ac_init, tprev, tr, tw, (T)R.M.p.ac_init_const);
+        else
+            acoustic_interior<SO, T, ARITH, true><<<interior_grid(blk), blk, 0, st>>>(ptrs(), R.M.G, R.M.ac, tprev, tr,
+                                                                                       tw, (T)0);
+        check();
+    }
+
+    // face launch geometry: threads along e2 (contiguous unless d == 2)
+    void face_dims(int d, int lo, int hi1, int hi2, dim3 &grid, dim3 &blk) const
+    {
+        blk = d == 2 ? dim3(8, 32) : dim3(128, 2);
+        const int n2 = hi2 - lo, n1 = hi1 - lo;
+        grid = dim3((n2 + blk.x - 1) / blk.x, (n1 + blk.y - 1) / blk.y);
+    }
+    template <typename T> void mirror(int field, int level, int d, const MirrorOps &ops, int lo, int himargin)
+    {
+        const Model &M = R.M;
+        const int e1 = d == 0 ? 1 : 0, e2 = d == 2 ? 1 : 2;
+        const int hi1 = M.G.dim[e1] - himargin, hi2 = M.G.dim[e2] - himargin;
+        if (hi1 <= lo || hi2 <= lo) return;
+        dim3 grid, blk;
+        face_dims(d, lo, hi1, hi2, grid, blk);
+        T *A = (T *)R.dev[field] + (long long)level * M.G.level;
+        face_mirror<T><<<grid, blk, 0, st>>>(A, M.G, ops, d, lo, hi1, hi2);
+        check();
+    }
+    template <typename T> void equation(const DevEq &eq, int lv0, int lv1, int d, int n, int lo, int himargin)
+    {
+        const Model &M = R.M;
+        const int e1 = d == 0 ? 1 : 0, e2 = d == 2 ? 1 : 2;
+        const int hi1 = M.G.dim[e1] - himargin, hi2 = M.G.dim[e2] - himargin;
+        if (hi1 <= lo || hi2 <= lo) return;
+        dim3 grid, blk;
+        face_dims(d, lo, hi1, hi2, grid, blk);
+        face_equation<T><<<grid, blk, 0, st>>>(ptrs(), M.G, eq, lv0, lv1, d, n, lo, hi1, hi2);
+        check();
+    }
+
+    // stress ghost loops in the reference's order (opesci/staggeredgrid.py:754-813)
+    template <typename T> void stress_bc(int t0, int t1, bool init)
+    {
+        const Model &M = R.M;
+        const int m = M.m;
+        static const int ORDER[6] = {F_TXX, F_TYY, F_TZZ, F_TXY, F_TYZ, F_TXZ};
+        static const int SH_A[3] = {0, 1, 0}, SH_B[3] = {1, 2, 2};
+        for (int fi = 0; fi < 6; ++fi)
+            for (int d = 0; d < 3; ++d) {
+                const int b_lo = m, b_hi = M.G.dim[d] - m - 1;
+                for (int side = 0; side < 2; ++side) {
+                    if (fi < 3 && fi == d) {
+                        // own-axis normal stress (opesci/fields.py:355-381), ranges [0,dim)
+                        MirrorOps ops;
+                        ops.count = 0;
+                        const int b = side == 0 ? b_lo : b_hi, dir = side == 0 ? -1 : 1;
+                        ops.dst[ops.count] = b; ops.src[ops.count++] = -1;
+                        for (int k = 1; k <= m - 1; ++k) { ops.dst[ops.count] = b + dir * k; ops.src[ops.count++] = b - dir * k; }
+                        mirror<T>(ORDER[fi], t1, d, ops, 0, 0);
+                    } else if (fi < 3) {
+                        // Levander recompute of the other normal stresses on this face from level t0
+                        // (opesci/fields.py:313-353; not in the initial pass, staggeredgrid.py:771-773)
+                        if (M.p.free_surface != 1 || init) continue;
+                        equation<T>(M.lev_stress_eq[d][fi], t0, t1, d, side == 0 ? b_lo : b_hi, m + 1, m + 1);
+                    } else {
+                        const int a = SH_A[fi - 3], bb = SH_B[fi - 3];
+                        if (d != a && d != bb) continue;
+                        // antisymmetric mirror of a shear stress (opesci/fields.py:366-381), ranges [0,dim)
+                        MirrorOps ops;
+                        ops.count = 0;
+                        for (int j = 0; j < m; ++j) {
+                            if (side == 0) { ops.dst[ops.count] = m - 1 - j; ops.src[ops.count++] = m + j; }
+                            else { ops.dst[ops.count] = b_hi + j; ops.src[ops.count++] = b_hi - 1 - j; }
+                        }
+                        mirror<T>(ORDER[fi], t1, d, ops, 0, 0);
+                    }
+                }
+            }
+    }
+
+    // velocity ghost loops in the reference's order (opesci/staggeredgrid.py:815-864)
+    template <typename T> void velocity_bc(int t1)
+    {
+        const Model &M = R.M;
+        const int m = M.m;
+        for (int d = 0; d < 3; ++d) {
+            int seq[3];
+            seq[0] = d;
+            for (int k = 0, n = 1; k < 3; ++k)
+                if (k != d) seq[n++] = k;
+            for (int si = 0; si < 3; ++si) {
+                const int a = seq[si];
+                for (int side = 0; side < 2; ++side) {
+                    if (M.p.free_surface == 1) {
+                        int n;
+                        if (a == d) n = side == 0 ? m - 1 : M.G.dim[d] - m - 1;
+                        else n = side == 0 ? m - 1 : M.G.dim[d] - m;
+                        // every operand and the result live on level t1 (slot 0 of the equation)
+                        equation<T>(M.lev_vel_eq[d][a][side], t1, t1, d, n, 1, 1);
+                    } else if (M.p.free_surface == 2) {
+                        // Robertsson: m ghost layers := 0 (opesci/fields.py:243-259)
+                        MirrorOps ops;
+                        ops.count = 0;
+                        for (int j = 0; j < m; ++j) {
+                            int n;
+                            if (side == 0) n = m - 1 - j;
+                            else n = (a == d ? M.G.dim[d] - m - 1 : M.G.dim[d] - m) + j;
+                            ops.dst[ops.count] = n; ops.src[ops.count++] = -1;
+                        }
+                        mirror<T>(VEL_OF_AXIS[a], t1, d, ops, 1, 1);
+                    }
+                }
+            }
+        }
+    }
+
+    template <int SO, typename T, int ARITH> void staggered_step(int ti)
+    {
+        const int t0 = ti % 2, t1 = (t0 + 1) % 2;   // opesci/regulargrid.py:408-433
+        stress<SO, T, ARITH>(t0, t1);
+        stress_bc<T>(t0, t1, false);
+        velocity<SO, T, ARITH>(t0, t1);
+        velocity_bc<T>(t1);
+    }
+    template <int SO, typename T, int ARITH> void acoustic_step(int ti)
+    {
+        const int t0 = ti % 3, t1 = (t0 + 1) % 3, t2 = (t1 + 1) % 3;
+        acoustic<SO, T, ARITH>(t0, t1, t2, false);
+    }
+};
+
+// ------------------------------------------------------------------ execute
+template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, double *loop_seconds)
+{
+    const Model &M = R.M;
+    const OpesciB200Params &p = M.p;
+    Stepper S(R, st);
+    // analytic initialisation of level 0 (staggeredgrid.py:612-659 / regulargrid.py:498-528)
+    for (int f = 0; f < p.nfields; ++f) {
+        Range3 rg;
+        for (int d = 0; d < 3; ++d) { rg.lo[d] = p.fields[f].lo[d]; rg.hi[d] = p.fields[f].hi[d]; }
+        if (rg.hi[0] <= rg.lo[0] || rg.hi[1] <= rg.lo[1] || rg.hi[2] <= rg.lo[2]) continue;
+        dim3 blk(64, 4);
+        dim3 grid((rg.hi[2] - rg.lo[2] + blk.x - 1) / blk.x, (rg.hi[1] - rg.lo[1] + blk.y - 1) / blk.y, rg.hi[0] - rg.lo[0]);
+        init_field<T><<<grid, blk, 0, st>>>((T *)R.dev[f], M.G, rg, R.d_prog + 2 * f);
+        S.check();
+    }
+    const bool staggered = p.kind == OPESCI_KIND_STAGGERED_ELASTIC;
+    const int period = staggered ? 2 : 3;
+    if (staggered) {
+        S.template stress_bc<T>(0, 0, true);   // initialise_bc (staggeredgrid.py:866-879)
+        S.template velocity_bc<T>(0);
+    } else {
+        S.template acoustic<SO, T, ARITH>(0, 0, 1, true);
+    }
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (S.err != cudaSuccess) return fail("kernel launch failed during initialisation: %s", cudaGetErrorString(S.err));
+
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    const int nsteps = p.ntsteps;
+    const bool use_graph = !(p.flags & OPESCI_NO_CUDA_GRAPH) && nsteps >= 2 * period;
+    long long per_period = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    if (use_graph) {
+        // one period of steps (time-level indices repeat with it) captured once, replayed
+        CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const long long before = S.launches;
+        for (int ti = 0; ti < period; ++ti) {
+            if (staggered) S.template staggered_step<SO, T, ARITH>(ti);
+            else S.template acoustic_step<SO, T, ARITH>(ti);
+        }
+        per_period = S.launches - before;
+        CUDA_OK(cudaStreamEndCapture(st, &graph));
+        CUDA_OK(cudaGraphInstantiate(&gexec, graph, 0));
+        S.launches = before;
+    }
+    CUDA_OK(cudaEventRecord(e0, st));
+    int ti = 0;
+    if (use_graph)
+        for (; ti + period <= nsteps; ti += period) {
+            CUDA_OK(cudaGraphLaunch(gexec, st));
+            S.launches += per_period;
+        }
+    for (; ti < nsteps; ++ti) {
+        if (staggered) S.template staggered_step<SO, T, ARITH>(ti);
+        else S.template acoustic_step<SO, T, ARITH>(ti);
+    }
+    CUDA_OK(cudaEventRecord(e1, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (S.err != cudaSuccess) return fail("kernel launch failed in the time loop: %s", cudaGetErrorString(S.err));
+    CUDA_OK(cudaGetLastError());
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    *loop_seconds = ms * 1e-3;
+    g_launches = S.launches;
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
+}
+
+template <typename T, int ARITH> int dispatch_so(Run &R, cudaStream_t st, double *secs)
+{
+    switch (R.M.p.so) {
+    case 2: return run_model<2, T, ARITH>(R, st, secs);
+    case 4: return run_model<4, T, ARITH>(R, st, secs);
+    case 6: return run_model<6, T, ARITH>(R, st, secs);
+    case 8: return run_model<8, T, ARITH>(R, st, secs);
+    case 10: return run_model<10, T, ARITH>(R, st, secs);
+    case 12: return run_model<12, T, ARITH>(R, st, secs);
+    }
+    return fail("unsupported spatial order");
+}
+
+int dispatch(Run &R, cudaStream_t st, double *secs)
+{
+    const bool fast = (R.M.p.flags & OPESCI_ARITH_MASK) == OPESCI_ARITH_FAST;
+    if (R.M.p.is_double)
+        return fast ? dispatch_so<double, OPESCI_ARITH_FAST>(R, st, secs) : dispatch_so<double, OPESCI_ARITH_REFERENCE>(R, st, secs);
+    return fast ? dispatch_so<float, OPESCI_ARITH_FAST>(R, st, secs) : dispatch_so<float, OPESCI_ARITH_REFERENCE>(R, st, secs);
+}
+
+void release(Run *R)
+{
+    for (int f = 0; f < OPESCI_MAX_FIELDS; ++f) {
+        if (R->dev[f]) cudaFree(R->dev[f]);
+        if (R->host[f]) {
+            if (R->host_pinned) cudaFreeHost(R->host[f]);
+            else free(R->host[f]);
+        }
+    }
+    if (R->d_tables) cudaFree(R->d_tables);
+    if (R->d_prog) cudaFree(R->d_prog);
+    delete R;
+}
+
+// upload tables + programs
+int upload_programs(Run &R)
+{
+    const Model &M = R.M;
+    const size_t nt = M.tables.size();
+    CUDA_OK(cudaMalloc(&R.d_tables, (nt ? nt : 1) * sizeof(double)));
+    if (nt) CUDA_OK(cudaMemcpy(R.d_tables, M.tables.data(), nt * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<DevProgram> progs(2 * (size_t)M.p.nfields);
+    for (int f = 0; f < M.p.nfields; ++f)
+        for (int w = 0; w < 2; ++w) {
+            const OpesciSolProgram &src = w ? M.p.fields[f].final_ : M.p.fields[f].init;
+            DevProgram &dst = progs[2 * f + w];
+            memset(&dst, 0, sizeof dst);
+            dst.n_instr = src.n_instr;
+            dst.n_tables = src.n_tables;
+            for (int t = 0; t < src.n_tables; ++t) {
+                dst.table_axis[t] = src.table_axis[t];
+                dst.table[t] = R.d_tables + M.table_off[f][w][t];
+            }
+            for (int i = 0; i < src.n_instr; ++i) dst.instr[i] = src.instr[i];
+        }
+    CUDA_OK(cudaMalloc(&R.d_prog, progs.size() * sizeof(DevProgram)));
+    CUDA_OK(cudaMemcpy(R.d_prog, progs.data(), progs.size() * sizeof(DevProgram), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+Run *find_run(OpesciGrid *grid)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_runs.find(grid->field[0]);
+    return it == g_runs.end() ? nullptr : it->second;
+}
+
+template <typename T> int l2_sums(Run &R, const void *const *level_base_dev, double *sums)
+{
+    const Model &M = R.M;
+    cudaStream_t st = 0;
+    double *d_out = nullptr, *d_partial = nullptr;
+    CUDA_OK(cudaMalloc(&d_out, OPESCI_MAX_FIELDS * sizeof(double)));
+    CUDA_OK(cudaMemset(d_out, 0, OPESCI_MAX_FIELDS * sizeof(double)));
+    size_t max_blocks = 1;
+    dim3 blk(64, 4);
+    std::vector<dim3> grids(M.p.nfields);
+    for (int f = 0; f < M.p.nfields; ++f) {
+        const OpesciFieldSpec &fs = M.p.fields[f];
+        const int nz = fs.l2_hi[2] - fs.l2_lo[2], ny = fs.l2_hi[1] - fs.l2_lo[1], nx = fs.l2_hi[0] - fs.l2_lo[0];
+        grids[f] = dim3(nz > 0 ? (nz + blk.x - 1) / blk.x : 0, ny > 0 ? (ny + blk.y - 1) / blk.y : 0, nx > 0 ? nx : 0);
+        const size_t nb = (size_t)grids[f].x * grids[f].y * grids[f].z;
+        if (nb > max_blocks) max_blocks = nb;
+    }
+    CUDA_OK(cudaMalloc(&d_partial, max_blocks * sizeof(double)));
+    for (int f = 0; f < M.p.nfields; ++f) {
+        const size_t nb = (size_t)grids[f].x * grids[f].y * grids[f].z;
+        if (nb == 0) continue;
+        Range3 rg;
+        for (int d = 0; d < 3; ++d) { rg.lo[d] = M.p.fields[f].l2_lo[d]; rg.hi[d] = M.p.fields[f].l2_hi[d]; }
+        l2_partial<T><<<grids[f], blk, 0, st>>>((const T *)level_base_dev[f], M.G, rg, R.d_prog + 2 * f + 1, d_partial);
+        l2_final<<<1, 1024, 0, st>>>(d_partial, nb, d_out + f);
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpy(sums, d_out, OPESCI_MAX_FIELDS * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d_out);
+    cudaFree(d_partial);
+    return 0;
+}
+
+// L2 sums of the level `ntsteps % 2` (the reference's `ti`, also for tp == 3: regulargrid.py:664)
+int convergence_sums(OpesciGrid *grid, double *sums, Model **model_out)
+{
+    Run *R = find_run(grid);
+    Run *tmp = nullptr;
+    std::vector<void *> uploaded;
+    const void *base[OPESCI_MAX_FIELDS] = {};
+    if (!R) {
+        // arrays this library did not produce: the reference semantics are "read the host arrays
+        // in *grid" -- upload level ti and reduce on the device
+        if (!g_model.configured) return fail("opesci_convergence: not configured");
+        tmp = new Run();
+        tmp->M = g_model;
+        if (upload_programs(*tmp)) { release(tmp); return 1; }
+        R = tmp;
+    }
+    const Model &M = R->M;
+    const int ti = M.p.ntsteps % 2;
+    const size_t esz = M.p.is_double ? 8 : 4;
+    const size_t lvl_bytes = (size_t)M.G.level * esz;
+    for (int f = 0; f < M.p.nfields; ++f) {
+        if (!tmp) {
+            base[f] = (const char *)R->dev[f] + (size_t)ti * lvl_bytes;
+        } else {
+            void *d = nullptr;
+            if (cudaMalloc(&d, lvl_bytes) != cudaSuccess ||
+                cudaMemcpy(d, (const char *)grid->field[f] + (size_t)ti * lvl_bytes, lvl_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+                for (void *u : uploaded) cudaFree(u);
+                release(tmp);
+                return fail("opesci_convergence: cannot upload host arrays (%s)", cudaGetErrorString(cudaGetLastError()));
+            }
+            uploaded.push_back(d);
+            base[f] = d;
+        }
+    }
+    int rc = M.p.is_double ? l2_sums<double>(*R, base, sums) : l2_sums<float>(*R, base, sums);
+    for (void *u : uploaded) cudaFree(u);
+    if (model_out) *model_out = &g_model;
+    if (tmp) release(tmp);
+    return rc;
+}
+
+}  // namespace
+
+// ==================================================================== C ABI
+extern "C" {
+
+const char *opesci_b200_last_error(void) { return g_err; }
+int opesci_b200_is_cuda(void) { return 1; }
+
+int opesci_b200_configure(const OpesciB200Params *params)
+{
+    if (!params || params->struct_size != sizeof(OpesciB200Params))
+        return fail("opesci_b200_configure: struct_size mismatch (header / binding out of date)");
+    if (params->so < 2 || params->so > 12 || (params->so & 1)) return fail("opesci_b200_configure: so must be even, 2..12");
+    for (int d = 0; d < 3; ++d)
+        if (params->dim[d] < 2 * (params->so / 2) + 1) return fail("opesci_b200_configure: grid too small for the stencil");
+    Model &M = g_model;
+    M = Model();
+    M.p = *params;
+    M.m = params->so / 2;
+    for (int d = 0; d < 3; ++d) M.G.dim[d] = params->dim[d];
+    M.G.m = M.m;
+    M.G.s[0] = (long long)params->dim[1] * params->dim[2];
+    M.G.s[1] = params->dim[2];
+    M.G.s[2] = 1;
+    M.G.level = (long long)params->dim[0] * params->dim[1] * params->dim[2];
+    memcpy(M.sc.sn, params->c_stress_normal, sizeof M.sc.sn);
+    memcpy(M.sc.ss, params->c_stress_shear, sizeof M.sc.ss);
+    memcpy(M.sc.v, params->c_velocity, sizeof M.sc.v);
+    for (int d = 0; d < 3; ++d) {
+        M.ac.present[d] = M.ac_init.present[d] = 0;
+        for (int k = 0; k < OPESCI_MAX_M; ++k) {
+            M.ac.c[d][k] = params->ac_coef[d][k];
+            M.ac_init.c[d][k] = params->ac_init_coef[d][k];
+            if (k < M.m && params->ac_coef[d][k] != 0.0f) M.ac.present[d] = 1;
+            if (k < M.m && params->ac_init_coef[d][k] != 0.0f) M.ac_init.present[d] = 1;
+        }
+    }
+    M.ac.centre = params->ac_centre;
+    M.ac_init.centre = params->ac_init_centre;
+    // private copy of the 1-D tables (the caller's arrays need not outlive this call)
+    for (int f = 0; f < params->nfields; ++f)
+        for (int w = 0; w < 2; ++w) {
+            const OpesciSolProgram &pr = w ? params->fields[f].final_ : params->fields[f].init;
+            if (pr.n_instr > OPESCI_MAX_PROG || pr.n_tables > OPESCI_MAX_TABLES) return fail("solution program too large");
+            M.table_off[f][w].clear();
+            for (int t = 0; t < pr.n_tables; ++t) {
+                const int ax = pr.table_axis[t];
+                if (ax < 0 || ax > 2 || !pr.table[t]) return fail("bad solution table");
+                M.table_off[f][w].push_back(M.tables.size());
+                M.tables.insert(M.tables.end(), pr.table[t], pr.table[t] + params->dim[ax]);
+            }
+        }
+    for (int f = 0; f < OPESCI_MAX_FIELDS; ++f)
+        for (int w = 0; w < 2; ++w) {
+            OpesciSolProgram &pr = w ? M.p.fields[f].final_ : M.p.fields[f].init;
+            for (int t = 0; t < OPESCI_MAX_TABLES; ++t) pr.table[t] = nullptr;   // host pointers are not kept
+        }
+    if (params->kind == OPESCI_KIND_STAGGERED_ELASTIC) {
+        if (params->nfields != 9 || params->nlevels != 2) return fail("staggered: need 9 fields, 2 levels");
+        if (params->free_surface == 1) {
+            if (params->so != 4) return fail("Levander free surface needs so == 4");
+            build_levander(M);
+        }
+    } else if (params->kind == OPESCI_KIND_REGULAR_ACOUSTIC) {
+        if (params->nfields != 1 || params->nlevels != 3) return fail("regular: need 1 field, 3 levels");
+    } else {
+        return fail("opesci_b200_configure: unknown kind");
+    }
+    M.configured = true;
+    g_err[0] = 0;
+    return 0;
+}
+
+int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
+{
+    if (!g_model.configured) return fail("opesci_execute: opesci_b200_configure was not called");
+    const auto wall0 = std::chrono::steady_clock::now();
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("opesci_execute: no CUDA device (this library has no CPU fallback)");
+    Run *R = new Run();
+    R->M = g_model;
+    const OpesciB200Params &p = R->M.p;
+    const size_t esz = p.is_double ? 8 : 4;
+    R->bytes_per_field = (size_t)R->M.G.level * p.nlevels * esz;
+    cudaStream_t st;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { release(R); return fail("cudaStreamCreate failed"); }
+    auto bail = [&](int rc) { cudaStreamDestroy(st); release(R); return rc; };
+    for (int f = 0; f < p.nfields; ++f) {
+        if (cudaMalloc(&R->dev[f], R->bytes_per_field) != cudaSuccess)
+            return bail(fail("opesci_execute: cudaMalloc of a field failed (%s)", cudaGetErrorString(cudaGetLastError())));
+        // regulargrid.py:489-490 allocates without clearing; de-facto contract "buffers start as 0"
+        if (cudaMemsetAsync(R->dev[f], 0, R->bytes_per_field, st) != cudaSuccess) return bail(fail("cudaMemset failed"));
+    }
+    if (upload_programs(*R)) return bail(1);
+    double secs = 0.0;
+    if (dispatch(*R, st, &secs)) return bail(1);
+    g_loop_seconds = secs;
+    const int mirror = p.flags & OPESCI_HOST_MIRROR_MASK;
+    if (mirror == OPESCI_HOST_MIRROR_FULL) {
+        for (int f = 0; f < p.nfields; ++f) {
+            // pinned host arrays: the D2H copy runs at PCIe speed
+            if (cudaMallocHost(&R->host[f], R->bytes_per_field) == cudaSuccess) {
+                R->host_pinned = true;
+            } else {
+                cudaGetLastError();
+                if (R->host_pinned) return bail(fail("opesci_execute: pinned host allocation failed"));
+                if (posix_memalign(&R->host[f], 4096, R->bytes_per_field) != 0) return bail(fail("opesci_execute: host allocation failed"));
+            }
+            if (cudaMemcpyAsync(R->host[f], R->dev[f], R->bytes_per_field, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                return bail(fail("opesci_execute: D2H copy failed"));
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) return bail(fail("opesci_execute: D2H copy failed (%s)", cudaGetErrorString(cudaGetLastError())));
+        for (int f = 0; f < p.nfields; ++f) grid->field[f] = R->host[f];   // regulargrid.py:445-453
+    } else {
+        for (int f = 0; f < p.nfields; ++f) grid->field[f] = R->dev[f];
+    }
+    cudaStreamDestroy(st);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_runs[grid->field[0]] = R;
+    }
+    if (profiling) {
+        const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+        const double pts = (double)(p.dim[0] - 2 * R->M.m) * (p.dim[1] - 2 * R->M.m) * (p.dim[2] - 2 * R->M.m);
+        const double flop_per_pt = p.kind == OPESCI_KIND_STAGGERED_ELASTIC ? 48.0 * p.so : 4.0 * p.so + 3.0;
+        profiling->g_rtime = (float)secs;
+        profiling->g_ptime = (float)wall;
+        profiling->g_mflops = secs > 0 ? (float)(pts * p.ntsteps * flop_per_pt / secs * 1e-6) : 0.f;
+    }
+    return 0;
+}
+
+int opesci_b200_convergence_f64(OpesciGrid *grid, double *out_l2)
+{
+    double sums[OPESCI_MAX_FIELDS];
+    Run *R = find_run(grid);
+    const Model &M = R ? R->M : g_model;
+    if (convergence_sums(grid, sums, nullptr)) return 1;
+    for (int f = 0; f < M.p.nfields; ++f) out_l2[f] = sqrt(sums[f] * (double)(float)M.p.volume_literal);
+    return 0;
+}
+
+int opesci_convergence(OpesciGrid *grid, OpesciConvergence *conv)
+{
+    // staggeredgrid.py:892-945: conv->F_l2 = pow(F_l2 * volume_literal, 0.5) in real_t.  The
+    // sum is accumulated in double by a deterministic tree (the reference accumulates serially
+    // in real_t, which loses digits on large grids: SURVEY.md 7 "hard parts").
+    double sums[OPESCI_MAX_FIELDS];
+    Run *R = find_run(grid);
+    const Model &M = R ? R->M : g_model;
+    if (convergence_sums(grid, sums, nullptr)) return 1;
+    for (int f = 0; f < M.p.nfields; ++f) {
+        if (M.p.is_double) conv->f64[f] = sqrt(sums[f] * (double)(float)M.p.volume_literal);
+        else conv->f32[f] = (float)sqrt((double)((float)sums[f] * (float)M.p.volume_literal));
+    }
+    return 0;
+}
+
+int opesci_free(OpesciGrid *grid)
+{
+    Run *R = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_runs.find(grid->field[0]);
+        if (it != g_runs.end()) { R = it->second; g_runs.erase(it); }
+    }
+    if (!R) return fail("opesci_free: arrays were not allocated by opesci_execute");
+    const int n = R->M.p.nfields;
+    release(R);
+    for (int f = 0; f < n; ++f) grid->field[f] = nullptr;
+    return 0;
+}
+
+int opesci_b200_last_timing(double *loop_seconds, double *points_per_step, int64_t *kernel_launches)
+{
+    const Model &M = g_model;
+    if (loop_seconds) *loop_seconds = g_loop_seconds;
+    if (points_per_step) *points_per_step = (double)(M.p.dim[0] - 2 * M.m) * (M.p.dim[1] - 2 * M.m) * (M.p.dim[2] - 2 * M.m);
+    if (kernel_launches) *kernel_launches = g_launches;
+    return 0;
+}
+
+}  // extern "C"

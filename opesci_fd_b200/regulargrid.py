@@ -29,6 +29,12 @@ def _frac(x):
     return Fraction(float(x))
 
 
+def _same_field(a, b):
+    """sympy may hand back an equal-by-name symbol created earlier in the process (its caches
+    key on structural equality), so fields are compared by label, never by identity."""
+    return a is not None and b is not None and str(a.label) == str(b.label)
+
+
 class RegularGrid(Grid):
     _papi_events = []
     _switches = ['omp', 'ivdep', 'simd', 'double', 'expand', 'eval_const',
@@ -216,12 +222,12 @@ class RegularGrid(Grid):
         self.eq = list(equations)
         field = self.fields[0]
         eq = self.eq[0]
-        if not (isinstance(eq.lhs, DDerivative) and eq.lhs.field is field and eq.lhs.axis == 0
+        if not (isinstance(eq.lhs, DDerivative) and _same_field(eq.lhs.field, field) and eq.lhs.axis == 0
                 and eq.lhs.order == 2):
             raise NotImplementedError("RegularGrid on B200 supports d2u/dt2 = sum_d w_d d2u/dx_d2 only")
         weights = [0] * self.dimension
         for d, c in self._linear_coefficients(eq).items():
-            if d.field is not field or d.order != 2 or d.axis == 0:
+            if not _same_field(d.field, field) or d.order != 2 or d.axis == 0:
                 raise NotImplementedError("RegularGrid on B200: unsupported term %s" % d)
             weights[d.axis - 1] = weights[d.axis - 1] + c
         self.axis_weights = weights

@@ -21,7 +21,7 @@ from . import abi, cexpr
 from .codeprinter import ccode, literal
 from .derivative import DDerivative
 from .fields import SField, VField
-from .regulargrid import RegularGrid, _frac
+from .regulargrid import RegularGrid, _frac, _same_field
 from .util import staggered_first_weights
 
 __all__ = ['StaggeredGrid']
@@ -139,7 +139,7 @@ class StaggeredGrid(RegularGrid):
         self.pde = {}
         for field, eq in zip(self.fields, self.eq):
             lhs = eq.lhs
-            if not (isinstance(lhs, DDerivative) and lhs.field is field and lhs.axis == 0 and lhs.order == 1):
+            if not (isinstance(lhs, DDerivative) and _same_field(lhs.field, field) and lhs.axis == 0 and lhs.order == 1):
                 raise NotImplementedError("equation %s: left side must be d%s/dt" % (eq, field.label))
             field.set_dt(eq.rhs)
             coefs = self._linear_coefficients(eq)
@@ -147,21 +147,21 @@ class StaggeredGrid(RegularGrid):
             for d, c in coefs.items():
                 if d.order != 1 or d.axis == 0:
                     raise NotImplementedError("unsupported derivative %s" % d)
-                table[(d.field, d.axis)] = c
+                table[(str(d.field.label), d.axis)] = c
             # expected sparsity
             if isinstance(field, VField):
                 a = field.direction
-                want = {(stress_of(a, d), d) for d in (1, 2, 3)}
+                want = {(str(stress_of(a, d).label), d) for d in (1, 2, 3)}
             elif field.direction[0] == field.direction[1]:
-                want = {(vel[d], d) for d in (1, 2, 3)}
+                want = {(str(vel[d].label), d) for d in (1, 2, 3)}
             else:
                 a, b = field.direction
-                want = {(vel[a], b), (vel[b], a)}
+                want = {(str(vel[a].label), b), (str(vel[b].label), a)}
             if set(table) != want:
                 raise NotImplementedError(
                     "equation for %s is not of velocity-stress form (B200 kernels are fixed-function; "
                     "general PDEs are SURVEY.md 8f item 4)" % field.label)
-            self.pde[field] = table
+            self.pde[str(field.label)] = table
 
     def set_free_surface_boundary(self, dimension, side):
         """reference: staggeredgrid.py:214-232.  Levander for so == 4, Robertsson otherwise."""
@@ -214,6 +214,9 @@ class StaggeredGrid(RegularGrid):
         def val(expr):
             return _frac(self._value(expr))
 
+        def pde(field, operand, axis):
+            return self.pde[str(field.label)][(str(operand.label), axis)]
+
         def fill(dst, coef, d):
             for k in range(m):
                 dst[k] = literal(float(ck[k] * dt / dx[d] * coef))
@@ -222,13 +225,13 @@ class StaggeredGrid(RegularGrid):
         M = {}
         for a in (1, 2, 3):
             for d in (1, 2, 3):
-                M[(a, d)] = val(self.pde[normal[a]][(vel[d], d)])
+                M[(a, d)] = val(pde(normal[a], vel[d], d))
                 fill(p.c_stress_normal[a - 1][d - 1], M[(a, d)], d)
                 g = normal[a] if a == d else shear[tuple(sorted((a, d)))]
-                fill(p.c_velocity[a - 1][d - 1], val(self.pde[vel[a]][(g, d)]), d)
+                fill(p.c_velocity[a - 1][d - 1], val(pde(vel[a], g, d)), d)
         for s, (a, b) in enumerate(_SHEAR):
-            fill(p.c_stress_shear[s][0], val(self.pde[shear[(a, b)]][(vel[a], b)]), b)
-            fill(p.c_stress_shear[s][1], val(self.pde[shear[(a, b)]][(vel[b], a)]), a)
+            fill(p.c_stress_shear[s][0], val(pde(shear[(a, b)], vel[a], b)), b)
+            fill(p.c_stress_shear[s][1], val(pde(shear[(a, b)], vel[b], a)), a)
         # Levander free surface (so == 4): eliminate d_d V_d with T_dd' = 0 (fields.py:313-353)
         # and build the ghost velocities from 2nd-order differences (fields.py:208-242)
         if so == 4:
@@ -244,7 +247,7 @@ class StaggeredGrid(RegularGrid):
                     ratio = float(dx[d] / dx[e])
                     p.lev_vnormal[d - 1][e - 1] = literal(float(M[(d, e)] / M[(d, d)] * dx[d] / dx[e]))
                     sh = shear[tuple(sorted((d, e)))]
-                    c_tang = val(self.pde[sh][(vel[d], e)]) / val(self.pde[sh][(vel[e], d)])
+                    c_tang = val(pde(sh, vel[d], e)) / val(pde(sh, vel[e], d))
                     p.lev_vtang[d - 1][e - 1] = literal(float(c_tang) * ratio)
         # init / L2: loops stop one short on staggered axes; coordinates are half-shifted there
         # (staggeredgrid.py:632-641, 918-927); first time dt/2 for velocities (staggeredgrid.py:647)
