@@ -125,7 +125,8 @@ typedef struct OpesciB200Params {
     int32_t converge;            /* switch `converge` */
     int32_t free_surface;        /* 1: Levander (so==4), 2: Robertsson (so!=4), 0: none (staggeredgrid.py:223-226) */
     int32_t flags;
-    int32_t reserved_i[3];
+    int32_t warmup_steps;        /* the first `warmup_steps` of `ntsteps` are excluded from the loop timing */
+    int32_t reserved_i[2];
     double dt;
     double dx[3];
     double volume_literal;       /* dx1*dx2*dx3 as printed (float literal) for the L2 scale */
@@ -173,6 +174,11 @@ const char *opesci_b200_last_error(void);
 int opesci_b200_convergence_f64(OpesciGrid *grid, double *out_l2);
 /* timing of the last opesci_execute: seconds in the time loop (device events) and point updates */
 int opesci_b200_last_timing(double *loop_seconds, double *points_per_step, int64_t *kernel_launches);
+/* Average device time (ms, CUDA events on the launching stream) of each interior kernel of one
+ * time step, measured by re-launching it `reps` times on the resident fields of `grid`:
+ * out_ms[0] = stress (or fused stress+velocity) kernel, out_ms[1] = velocity kernel (0 if fused),
+ * out_ms[2] = all ghost-cell loops of one step.  Advances the fields; call it last. */
+int opesci_b200_time_kernels(OpesciGrid *grid, int reps, double *out_ms);
 /* 1 if this library was built with the CUDA kernels (0 for the CPU oracle build) */
 int opesci_b200_is_cuda(void);
 

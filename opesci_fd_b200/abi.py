@@ -64,7 +64,7 @@ class OpesciB200Params(Structure):
         ("struct_size", c_uint32), ("kind", c_int32), ("so", c_int32), ("is_double", c_int32),
         ("dim", c_int32 * 3), ("ntsteps", c_int32), ("nfields", c_int32), ("nlevels", c_int32),
         ("converge", c_int32), ("free_surface", c_int32), ("flags", c_int32),
-        ("reserved_i", c_int32 * 3),
+        ("warmup_steps", c_int32), ("reserved_i", c_int32 * 2),
         ("dt", c_double), ("dx", c_double * 3), ("volume_literal", c_double),
         ("c_stress_normal", ((c_float * OPESCI_MAX_M) * 3) * 3),
         ("c_stress_shear", ((c_float * OPESCI_MAX_M) * 2) * 3),
@@ -84,7 +84,7 @@ class OpesciB200Params(Structure):
 EXPORTED_SYMBOLS = [
     "opesci_b200_configure", "opesci_execute", "opesci_convergence", "opesci_free",
     "opesci_b200_last_error", "opesci_b200_convergence_f64", "opesci_b200_last_timing",
-    "opesci_b200_is_cuda",
+    "opesci_b200_is_cuda", "opesci_b200_time_kernels",
 ]
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -107,6 +107,9 @@ def bind(lib):
     lib.opesci_b200_convergence_f64.restype = ctypes.c_int
     lib.opesci_b200_last_timing.argtypes = [POINTER(c_double), POINTER(c_double), POINTER(c_int64)]
     lib.opesci_b200_last_timing.restype = ctypes.c_int
+    if hasattr(lib, "opesci_b200_time_kernels"):
+        lib.opesci_b200_time_kernels.argtypes = [POINTER(OpesciGrid), ctypes.c_int, POINTER(c_double)]
+        lib.opesci_b200_time_kernels.restype = ctypes.c_int
     lib.opesci_b200_is_cuda.argtypes = []
     lib.opesci_b200_is_cuda.restype = ctypes.c_int
     return lib

@@ -370,17 +370,30 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
         CUDA_OK(cudaGraphInstantiate(&gexec, graph, 0));
         S.launches = before;
     }
-    CUDA_OK(cudaEventRecord(e0, st));
+    // the first `warmup_steps` steps run untimed (bench contract)
+    int warm = p.warmup_steps > 0 ? p.warmup_steps : 0;
+    if (warm > nsteps) warm = nsteps;
     int ti = 0;
-    if (use_graph)
-        for (; ti + period <= nsteps; ti += period) {
-            CUDA_OK(cudaGraphLaunch(gexec, st));
-            S.launches += per_period;
+    auto run_steps = [&](int upto) -> int {
+        while (ti < upto) {
+            if (use_graph && ti % period == 0 && ti + period <= upto) {
+                CUDA_OK(cudaGraphLaunch(gexec, st));
+                S.launches += per_period;
+                ti += period;
+            } else {
+                if (staggered) S.template staggered_step<SO, T, ARITH>(ti);
+                else S.template acoustic_step<SO, T, ARITH>(ti);
+                ++ti;
+            }
         }
-    for (; ti < nsteps; ++ti) {
-        if (staggered) S.template staggered_step<SO, T, ARITH>(ti);
-        else S.template acoustic_step<SO, T, ARITH>(ti);
+        return 0;
+    };
+    if (warm > 0) {
+        if (run_steps(warm)) return 1;
+        S.launches = 0;
     }
+    CUDA_OK(cudaEventRecord(e0, st));
+    if (run_steps(nsteps)) return 1;
     CUDA_OK(cudaEventRecord(e1, st));
     CUDA_OK(cudaStreamSynchronize(st));
     if (S.err != cudaSuccess) return fail("kernel launch failed in the time loop: %s", cudaGetErrorString(S.err));
@@ -415,6 +428,52 @@ int dispatch(Run &R, cudaStream_t st, double *secs)
     if (R.M.p.is_double)
         return fast ? dispatch_so<double, OPESCI_ARITH_FAST>(R, st, secs) : dispatch_so<double, OPESCI_ARITH_REFERENCE>(R, st, secs);
     return fast ? dispatch_so<float, OPESCI_ARITH_FAST>(R, st, secs) : dispatch_so<float, OPESCI_ARITH_REFERENCE>(R, st, secs);
+}
+
+template <int SO, typename T, int ARITH> int time_kernels_impl(Run &R, int reps, double *out_ms)
+{
+    cudaStream_t st;
+    CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    Stepper S(R, st);
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    const bool staggered = R.M.p.kind == OPESCI_KIND_STAGGERED_ELASTIC;
+    out_ms[0] = out_ms[1] = out_ms[2] = 0.0;
+    float ms;
+    for (int phase = 0; phase < 3; ++phase) {
+        if (!staggered && phase > 0) break;
+        CUDA_OK(cudaStreamSynchronize(st));
+        CUDA_OK(cudaEventRecord(e0, st));
+        for (int r = 0; r < reps; ++r) {
+            const int ti = R.M.p.ntsteps + r, t0 = ti % 2, t1 = (t0 + 1) % 2;
+            if (!staggered) S.template acoustic_step<SO, T, ARITH>(ti);
+            else if (phase == 0) S.template stress<SO, T, ARITH>(t0, t1);
+            else if (phase == 1) S.template velocity<SO, T, ARITH>(t0, t1);
+            else { S.template stress_bc<T>(t0, t1, false); S.template velocity_bc<T>(t1); }
+        }
+        CUDA_OK(cudaEventRecord(e1, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        out_ms[phase] = ms / reps;
+    }
+    if (S.err != cudaSuccess) return fail("time_kernels: launch failed: %s", cudaGetErrorString(S.err));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaStreamDestroy(st);
+    return 0;
+}
+template <typename T, int ARITH> int time_kernels_so(Run &R, int reps, double *out_ms)
+{
+    switch (R.M.p.so) {
+    case 2: return time_kernels_impl<2, T, ARITH>(R, reps, out_ms);
+    case 4: return time_kernels_impl<4, T, ARITH>(R, reps, out_ms);
+    case 6: return time_kernels_impl<6, T, ARITH>(R, reps, out_ms);
+    case 8: return time_kernels_impl<8, T, ARITH>(R, reps, out_ms);
+    case 10: return time_kernels_impl<10, T, ARITH>(R, reps, out_ms);
+    case 12: return time_kernels_impl<12, T, ARITH>(R, reps, out_ms);
+    }
+    return fail("unsupported spatial order");
 }
 
 void release(Run *R)
@@ -711,6 +770,17 @@ int opesci_free(OpesciGrid *grid)
     release(R);
     for (int f = 0; f < n; ++f) grid->field[f] = nullptr;
     return 0;
+}
+
+int opesci_b200_time_kernels(OpesciGrid *grid, int reps, double *out_ms)
+{
+    Run *R = find_run(grid);
+    if (!R) return fail("opesci_b200_time_kernels: unknown grid");
+    if (reps < 1) reps = 1;
+    const bool fast = (R->M.p.flags & OPESCI_ARITH_MASK) == OPESCI_ARITH_FAST;
+    if (R->M.p.is_double)
+        return fast ? time_kernels_so<double, OPESCI_ARITH_FAST>(*R, reps, out_ms) : time_kernels_so<double, OPESCI_ARITH_REFERENCE>(*R, reps, out_ms);
+    return fast ? time_kernels_so<float, OPESCI_ARITH_FAST>(*R, reps, out_ms) : time_kernels_so<float, OPESCI_ARITH_REFERENCE>(*R, reps, out_ms);
 }
 
 int opesci_b200_last_timing(double *loop_seconds, double *points_per_step, int64_t *kernel_launches)

@@ -394,6 +394,12 @@ int opesci_free(OpesciGrid *grid)
     return 0;
 }
 
+int opesci_b200_time_kernels(OpesciGrid *grid, int reps, double *out_ms)
+{
+    (void)grid; (void)reps; (void)out_ms;
+    return fail("opesci_b200_time_kernels: CUDA library only");
+}
+
 int opesci_b200_last_timing(double *loop_seconds, double *points_per_step, int64_t *kernel_launches)
 {
     const Model *M = &g_model;

@@ -68,9 +68,9 @@ _ew("ew_mid_so8_f32", 8, (64, 64, 64), 0.003, 60, tags=["mid"])
 _ew("ew_mid_so4_f64", 4, (64, 64, 64), 0.003, 60, double=True, tags=["mid"])
 # --- CPU-baseline timing pairs (bench.py --impl reference): same grid, two step counts
 _ew("ew_bench_so4_f32_n256_s4", 4, (256, 256, 256), 0.001, 4, converge=False, tags=["bench"])
-_ew("ew_bench_so4_f32_n256_s24", 4, (256, 256, 256), 0.001, 24, converge=False, tags=["bench"])
+_ew("ew_bench_so4_f32_n256_s84", 4, (256, 256, 256), 0.001, 84, converge=False, tags=["bench"])
 _ew("ew_bench_so4_f32_n512_s2", 4, (512, 512, 512), 0.0005, 2, converge=False, tags=["bench"])
-_ew("ew_bench_so4_f32_n512_s8", 4, (512, 512, 512), 0.0005, 8, converge=False, tags=["bench"])
+_ew("ew_bench_so4_f32_n512_s34", 4, (512, 512, 512), 0.0005, 34, converge=False, tags=["bench"])
 
 
 def generate(name):

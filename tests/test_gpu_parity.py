@@ -49,18 +49,32 @@ def test_cuda_fast_arithmetic_within_tolerance_vs_golden(name, cuda_lib):
     grid.free()
 
 
-@pytest.mark.parametrize("name", ["ew_default_so4_f32", "ew_default_so8_f32", "ew_default_so4_f64",
-                                  "sw_default_so4_f32", "ew_mid_so4_f32", "ew_mid_so8_f32"])
-def test_cuda_reproduces_reference_l2_norms(name, cuda_lib):
-    """The reference's own default test cases (tests/eigenwave3d.py:149-167, 100^3 x 500 steps):
-    its analytic-eigenwave L2 output, reproduced from the device-resident fields."""
+@pytest.mark.parametrize("name", ["ew_default_so4_f32", "ew_default_so8_f32", "ew_default_so12_f32",
+                                  "ew_default_so4_f64", "sw_default_so4_f32", "ew_mid_so4_f32", "ew_mid_so8_f32"])
+def test_cuda_reproduces_reference_l2_norms(name, cuda_lib, oracle_lib):
+    """The reference's own default test cases (tests/eigenwave3d.py:149-167, 100^3 x 500 steps) and
+    the 64^3 x 60 cases: its analytic-eigenwave L2 output must be reproduced.
+
+    The reference accumulates the L2 sum serially in real_t (staggeredgrid.py:916,935), so its fp32
+    norms carry ~1e-3 relative accumulation noise.  To compare digit for digit, the reference's
+    exact norm arithmetic (the oracle's opesci_convergence, pinned bit-exactly on CPU) is applied to
+    the fields the GPU produced: if the GPU fields are bit-identical to the reference's, the
+    printed norms are identical to all 10 digits."""
+    import ctypes
     entry = load_norms()[name]
     cfg = entry["config"]
-    grid = make_grid(cfg, flags=abi.ARITH_REFERENCE | abi.HOST_MIRROR_NONE)
+    grid = make_grid(cfg, flags=abi.ARITH_REFERENCE | abi.HOST_MIRROR_FULL)
     grid.run(library=cuda_lib)
-    got = np.array(grid.convergence_f64())
-    # the reference accumulates serially in real_t: its fp32 norms carry ~1e-4 relative noise
-    np.testing.assert_allclose(got, np.array(entry["l2"]), rtol=3e-4 if not cfg["double"] else 2e-9)
+    conv = abi.OpesciConvergence()
+    params, keep = grid.build_params()
+    assert oracle_lib.opesci_b200_configure(ctypes.byref(params)) == 0
+    assert oracle_lib.opesci_convergence(ctypes.byref(grid._arg_grid), ctypes.byref(conv)) == 0
+    vals = conv.f64 if cfg["double"] else conv.f32
+    got = ["%.10f" % vals[k] for k in range(len(cfg["fields"]))]
+    assert got == entry["l2_printed"]
+    # the library's own (double-accumulated, deterministic) norms: same up to accumulation noise
+    got64 = np.array(grid.convergence_f64())
+    np.testing.assert_allclose(got64, np.array(entry["l2"]), rtol=3e-3 if not cfg["double"] else 2e-9)
     norms = grid.convergence()
     assert set(norms) == {"%s_l2" % f for f in cfg["fields"]}
     grid.free()
