@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 
+#include "fused.cuh"
 #include "kernels.cuh"
 
 using namespace opesci;
@@ -62,7 +63,11 @@ struct Run {
     bool host_pinned = false;
     double *d_tables = nullptr;
     DevProgram *d_prog = nullptr;   // [nfields][2]
-    size_t bytes_per_field = 0;
+    size_t bytes_per_field = 0;     // device bytes (pitched rows)
+    size_t host_bytes_per_field = 0;
+    bool fused = false;             // fused stress+velocity kernel in use
+    CUtensorMap tmap[3];            // U, V, W (both time levels; level selected through the x coordinate)
+    int xchunk = 0, nchunks = 1;
 };
 std::map<void *, Run *> g_runs;
 std::mutex g_mu;
@@ -307,13 +312,57 @@ struct Stepper {
         }
     }
 
+    // fused stress+velocity launch (fused.cuh); only instantiated for so <= 4, fp32
+    template <int SO, typename T, int ARITH> void fused(int t0, int t1)
+    {
+        if constexpr (SO <= 4 && sizeof(T) == 4) {
+            constexpr int M = SO / 2;
+            using K = FusedCfg<M>;
+            const Model &Md = R.M;
+            FusedArgs A;
+            A.F = ptrs(); A.G = Md.G; A.C = Md.sc; A.t0 = t0; A.t1 = t1; A.xchunk = R.xchunk;
+            dim3 grid((Md.G.dim[2] - 2 * M + K::CZ - 1) / K::CZ, (Md.G.dim[1] - 2 * M + K::CY - 1) / K::CY, R.nchunks);
+            fused_step<SO, ARITH><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
+            check();
+        }
+    }
+    // velocity update of the shell the fused kernel leaves out: interior minus [2m+1, dim-2m-1)^3
+    template <int SO, typename T, int ARITH> void velocity_shell(int t0, int t1)
+    {
+        const Model &Md = R.M;
+        const int m = Md.m;
+        int lo[3], hi[3], ilo[3], ihi[3];
+        for (int d = 0; d < 3; ++d) { lo[d] = m; hi[d] = Md.G.dim[d] - m; ilo[d] = 2 * m + 1; ihi[d] = Md.G.dim[d] - 2 * m - 1; }
+        for (int d = 0; d < 3; ++d)
+            for (int side = 0; side < 2; ++side) {
+                Range3 rg;
+                for (int e = 0; e < 3; ++e) {
+                    if (e < d) { rg.lo[e] = ilo[e]; rg.hi[e] = ihi[e]; }     // already covered by earlier slabs
+                    else if (e == d) { rg.lo[e] = side == 0 ? lo[e] : ihi[e]; rg.hi[e] = side == 0 ? ilo[e] : hi[e]; }
+                    else { rg.lo[e] = lo[e]; rg.hi[e] = hi[e]; }
+                }
+                if (rg.hi[0] <= rg.lo[0] || rg.hi[1] <= rg.lo[1] || rg.hi[2] <= rg.lo[2]) continue;
+                dim3 blk = d == 2 ? dim3(4, 64) : dim3(64, 4);
+                dim3 grid((rg.hi[2] - rg.lo[2] + blk.x - 1) / blk.x, (rg.hi[1] - rg.lo[1] + blk.y - 1) / blk.y, rg.hi[0] - rg.lo[0]);
+                velocity_box<SO, T, ARITH><<<grid, blk, 0, st>>>(ptrs(), Md.G, Md.sc, t0, t1, rg);
+                check();
+            }
+    }
+
     template <int SO, typename T, int ARITH> void staggered_step(int ti)
     {
         const int t0 = ti % 2, t1 = (t0 + 1) % 2;   // opesci/regulargrid.py:408-433
-        stress<SO, T, ARITH>(t0, t1);
-        stress_bc<T>(t0, t1, false);
-        velocity<SO, T, ARITH>(t0, t1);
-        velocity_bc<T>(t1);
+        if (R.fused) {
+            fused<SO, T, ARITH>(t0, t1);             // stress everywhere + velocity of the deep interior
+            stress_bc<T>(t0, t1, false);
+            velocity_shell<SO, T, ARITH>(t0, t1);    // velocity next to the faces, after the stress ghost loops
+            velocity_bc<T>(t1);
+        } else {
+            stress<SO, T, ARITH>(t0, t1);
+            stress_bc<T>(t0, t1, false);
+            velocity<SO, T, ARITH>(t0, t1);
+            velocity_bc<T>(t1);
+        }
     }
     template <int SO, typename T, int ARITH> void acoustic_step(int ti)
     {
@@ -321,6 +370,67 @@ struct Stepper {
         acoustic<SO, T, ARITH>(t0, t1, t2, false);
     }
 };
+
+
+// ------------------------------------------------------------------ fused path set-up
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int M, int ARITH> int set_fused_attr()
+{
+    CUDA_OK(cudaFuncSetAttribute(fused_step<2 * M, ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<M>::SMEM));
+    return 0;
+}
+
+int setup_fused(Run &R)
+{
+    const Model &M = R.M;
+    const OpesciB200Params &p = M.p;
+    R.fused = false;
+    if (p.kind != OPESCI_KIND_STAGGERED_ELASTIC || p.is_double || p.so > 4 || (p.flags & OPESCI_FORCE_UNFUSED)) return 0;
+    for (int d = 0; d < 3; ++d)
+        if (p.dim[d] < 6 * M.m + 4) return 0;   // no deep interior worth fusing
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+            return fail("cuTensorMapEncodeTiled not available from the driver");
+        encode = (EncodeTiledFn)fn;
+    }
+    const int m = M.m;
+    const int VZ = 64 + 2 * m, VY = 16 + 2 * m;
+    for (int f = 0; f < 3; ++f) {
+        cuuint64_t gdim[3] = {(cuuint64_t)p.dim[2], (cuuint64_t)p.dim[1], (cuuint64_t)p.dim[0] * p.nlevels};
+        cuuint64_t gstride[2] = {(cuuint64_t)M.G.s[1] * 4, (cuuint64_t)M.G.s[0] * 4};
+        cuuint32_t box[3] = {(cuuint32_t)VZ, (cuuint32_t)VY, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult rc = encode(&R.tmap[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, R.dev[f], gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed");
+    }
+    if (m == 1) { if (set_fused_attr<1, OPESCI_ARITH_REFERENCE>() || set_fused_attr<1, OPESCI_ARITH_FAST>()) return 1; }
+    else { if (set_fused_attr<2, OPESCI_ARITH_REFERENCE>() || set_fused_attr<2, OPESCI_ARITH_FAST>()) return 1; }
+    // x-chunks: enough CTAs to fill the machine in whole waves, few enough to keep the 2m-plane
+    // warm-up of every chunk negligible
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+    const int CZ = 64 - 2 * m, CY = 16 - 2 * m;
+    const long long tiles = (long long)((p.dim[2] - 2 * m + CZ - 1) / CZ) * ((p.dim[1] - 2 * m + CY - 1) / CY);
+    const int nx = p.dim[0] - 2 * m;
+    double best = -1.0;
+    for (int nc = 1; nc <= 16; ++nc) {
+        const int len = (nx + nc - 1) / nc;
+        if (len < 8 * m && nc > 1) break;
+        const double waves = (double)tiles * nc / nsm;
+        const double eff = waves / (double)((long long)(waves + 0.999999)) * len / (len + 2.0 * m + 2.0);
+        if (eff > best) { best = eff; R.nchunks = nc; R.xchunk = len; }
+    }
+    R.fused = true;
+    return 0;
+}
 
 // ------------------------------------------------------------------ execute
 template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, double *loop_seconds)
@@ -448,14 +558,18 @@ template <int SO, typename T, int ARITH> int time_kernels_impl(Run &R, int reps,
         for (int r = 0; r < reps; ++r) {
             const int ti = R.M.p.ntsteps + r, t0 = ti % 2, t1 = (t0 + 1) % 2;
             if (!staggered) S.template acoustic_step<SO, T, ARITH>(ti);
-            else if (phase == 0) S.template stress<SO, T, ARITH>(t0, t1);
-            else if (phase == 1) S.template velocity<SO, T, ARITH>(t0, t1);
-            else { S.template stress_bc<T>(t0, t1, false); S.template velocity_bc<T>(t1); }
+            else if (phase == 0) { if (R.fused) S.template fused<SO, T, ARITH>(t0, t1); else S.template stress<SO, T, ARITH>(t0, t1); }
+            else if (phase == 1) { if (R.fused) break; S.template velocity<SO, T, ARITH>(t0, t1); }
+            else {
+                S.template stress_bc<T>(t0, t1, false);
+                if (R.fused) S.template velocity_shell<SO, T, ARITH>(t0, t1);
+                S.template velocity_bc<T>(t1);
+            }
         }
         CUDA_OK(cudaEventRecord(e1, st));
         CUDA_OK(cudaStreamSynchronize(st));
         CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
-        out_ms[phase] = ms / reps;
+        out_ms[phase] = (R.fused && phase == 1) ? 0.0 : ms / reps;
     }
     if (S.err != cudaSuccess) return fail("time_kernels: launch failed: %s", cudaGetErrorString(S.err));
     cudaEventDestroy(e0);
@@ -576,13 +690,17 @@ int convergence_sums(OpesciGrid *grid, double *sums, Model **model_out)
     const int ti = M.p.ntsteps % 2;
     const size_t esz = M.p.is_double ? 8 : 4;
     const size_t lvl_bytes = (size_t)M.G.level * esz;
+    const size_t host_row = (size_t)M.p.dim[2] * esz, dev_row = (size_t)M.G.s[1] * esz;
+    const size_t rows = (size_t)M.p.dim[0] * M.p.dim[1];
+    const size_t host_lvl_bytes = rows * host_row;
     for (int f = 0; f < M.p.nfields; ++f) {
         if (!tmp) {
             base[f] = (const char *)R->dev[f] + (size_t)ti * lvl_bytes;
         } else {
             void *d = nullptr;
-            if (cudaMalloc(&d, lvl_bytes) != cudaSuccess ||
-                cudaMemcpy(d, (const char *)grid->field[f] + (size_t)ti * lvl_bytes, lvl_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+            if (cudaMalloc(&d, lvl_bytes) != cudaSuccess || cudaMemset(d, 0, lvl_bytes) != cudaSuccess ||
+                cudaMemcpy2D(d, dev_row, (const char *)grid->field[f] + (size_t)ti * host_lvl_bytes, host_row, host_row, rows,
+                             cudaMemcpyHostToDevice) != cudaSuccess) {
                 for (void *u : uploaded) cudaFree(u);
                 release(tmp);
                 return fail("opesci_convergence: cannot upload host arrays (%s)", cudaGetErrorString(cudaGetLastError()));
@@ -619,10 +737,13 @@ int opesci_b200_configure(const OpesciB200Params *params)
     M.m = params->so / 2;
     for (int d = 0; d < 3; ++d) M.G.dim[d] = params->dim[d];
     M.G.m = M.m;
-    M.G.s[0] = (long long)params->dim[1] * params->dim[2];
-    M.G.s[1] = params->dim[2];
+    // device rows are padded to a multiple of 32 elements (TMA needs 16-B row strides; 128-B rows
+    // keep tiles sector-aligned); the host arrays keep the reference's dense layout
+    const long long pitch = ((long long)params->dim[2] + 31) / 32 * 32;
+    M.G.s[0] = (long long)params->dim[1] * pitch;
+    M.G.s[1] = pitch;
     M.G.s[2] = 1;
-    M.G.level = (long long)params->dim[0] * params->dim[1] * params->dim[2];
+    M.G.level = (long long)params->dim[0] * params->dim[1] * pitch;
     memcpy(M.sc.sn, params->c_stress_normal, sizeof M.sc.sn);
     memcpy(M.sc.ss, params->c_stress_shear, sizeof M.sc.ss);
     memcpy(M.sc.v, params->c_velocity, sizeof M.sc.v);
@@ -683,6 +804,7 @@ int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
     const OpesciB200Params &p = R->M.p;
     const size_t esz = p.is_double ? 8 : 4;
     R->bytes_per_field = (size_t)R->M.G.level * p.nlevels * esz;
+    R->host_bytes_per_field = (size_t)p.dim[0] * p.dim[1] * p.dim[2] * p.nlevels * esz;
     cudaStream_t st;
     if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { release(R); return fail("cudaStreamCreate failed"); }
     auto bail = [&](int rc) { cudaStreamDestroy(st); release(R); return rc; };
@@ -693,6 +815,7 @@ int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
         if (cudaMemsetAsync(R->dev[f], 0, R->bytes_per_field, st) != cudaSuccess) return bail(fail("cudaMemset failed"));
     }
     if (upload_programs(*R)) return bail(1);
+    if (setup_fused(*R)) return bail(1);
     double secs = 0.0;
     if (dispatch(*R, st, &secs)) return bail(1);
     g_loop_seconds = secs;
@@ -700,14 +823,16 @@ int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
     if (mirror == OPESCI_HOST_MIRROR_FULL) {
         for (int f = 0; f < p.nfields; ++f) {
             // pinned host arrays: the D2H copy runs at PCIe speed
-            if (cudaMallocHost(&R->host[f], R->bytes_per_field) == cudaSuccess) {
+            if (cudaMallocHost(&R->host[f], R->host_bytes_per_field) == cudaSuccess) {
                 R->host_pinned = true;
             } else {
                 cudaGetLastError();
                 if (R->host_pinned) return bail(fail("opesci_execute: pinned host allocation failed"));
-                if (posix_memalign(&R->host[f], 4096, R->bytes_per_field) != 0) return bail(fail("opesci_execute: host allocation failed"));
+                if (posix_memalign(&R->host[f], 4096, R->host_bytes_per_field) != 0) return bail(fail("opesci_execute: host allocation failed"));
             }
-            if (cudaMemcpyAsync(R->host[f], R->dev[f], R->bytes_per_field, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            // dense host rows (reference layout [tp][dim1][dim2][dim3]) <- pitched device rows
+            if (cudaMemcpy2DAsync(R->host[f], (size_t)p.dim[2] * esz, R->dev[f], (size_t)R->M.G.s[1] * esz, (size_t)p.dim[2] * esz,
+                                  (size_t)p.nlevels * p.dim[0] * p.dim[1], cudaMemcpyDeviceToHost, st) != cudaSuccess)
                 return bail(fail("opesci_execute: D2H copy failed"));
         }
         if (cudaStreamSynchronize(st) != cudaSuccess) return bail(fail("opesci_execute: D2H copy failed (%s)", cudaGetErrorString(cudaGetLastError())));
