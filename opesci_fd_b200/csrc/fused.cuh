@@ -96,8 +96,12 @@ __device__ __forceinline__ T window_fast_arr(const T *v, const float *c)
 
 template <int M> struct FusedCfg {
     static constexpr int EZ = 64, EY = 16;                 // threads = stress tile (incl. recomputed halo)
-    static constexpr int CZ = EZ - 2 * M, CY = EY - 2 * M; // stored tile
-    static constexpr int VZ = EZ + 2 * M, VY = EY + 2 * M; // velocity tile delivered by TMA
+    // stored tile.  TMA needs the innermost box coordinate 16-B aligned (measured on B200: an
+    // unaligned start raises "illegal instruction"), so tiles advance in multiples of 4 floats
+    // along z and the box starts OFFZ >= M floats left of the stress tile.
+    static constexpr int CZ = (EZ - 2 * M) / 4 * 4, CY = EY - 2 * M;
+    static constexpr int OFFZ = (M + 3) / 4 * 4;
+    static constexpr int VZ = (EZ + M + OFFZ + 3) / 4 * 4, VY = EY + 2 * M;   // velocity tile delivered by TMA
     static constexpr int RD = 2 * M + 2;                   // velocity ring depth (planes)
     static constexpr int SR = 4;                           // in-plane stress ring slots
     static constexpr int VTILE = ((VZ * VY * 4 + 127) / 128) * 128;   // bytes, 128-B aligned for TMA
@@ -138,7 +142,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     const int xs_begin = max(M, xa - M), xs_end = min(G.dim[0] - M, xb + M);
     const int pbaseU = xs_begin - M, pbaseVW = xs_begin - M + 1;
     const int lastU = xs_end + M - 2, lastVW = xs_end + M - 1;
-    const int c0 = blockIdx.x * K::CZ - M, c1 = blockIdx.y * K::CY - M;     // TMA box origin (may be negative)
+    const int c0 = blockIdx.x * K::CZ - K::OFFZ, c1 = blockIdx.y * K::CY - M;   // TMA box origin (may be negative)
     const int lvl0 = A.t0 * G.dim[0];
     constexpr uint32_t TILE_BYTES = K::VZ * K::VY * 4;
 
@@ -152,8 +156,9 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
         const int slot = (plane - pbase) % K::RD;
         uint64_t *bar = &bars[f * K::RD + slot];
         mbar_arrive_expect_tx(bar, TILE_BYTES);
-        const CUtensorMap *tm = f == 0 ? &tmU : (f == 1 ? &tmV : &tmW);
-        tma_load_3d((void *)vtile(f, slot), tm, bar, c0, c1, lvl0 + plane);
+        if (f == 0) tma_load_3d((void *)vtile(0, slot), &tmU, bar, c0, c1, lvl0 + plane);
+        else if (f == 1) tma_load_3d((void *)vtile(1, slot), &tmV, bar, c0, c1, lvl0 + plane);
+        else tma_load_3d((void *)vtile(2, slot), &tmW, bar, c0, c1, lvl0 + plane);
     };
     if (tid == 0) {
         for (int k = 0; k < K::RD; ++k) {
@@ -164,7 +169,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     int waitedU = pbaseU - 1, waitedVW = pbaseVW - 1;
 
     const bool inb = ye < G.dim[1] && ze < G.dim[2];
-    const bool core = ty >= M && ty < K::EY - M && tz >= M && tz < K::EZ - M;
+    const bool core = ty >= M && ty < M + K::CY && tz >= M && tz < M + K::CZ;
     const bool st_yz = core && ye >= M && ye < G.dim[1] - M && ze >= M && ze < G.dim[2] - M;
     const bool vf_yz = core && ye >= 2 * M + 1 && ye < G.dim[1] - 2 * M - 1 && ze >= 2 * M + 1 && ze < G.dim[2] - 2 * M - 1;
     const int xv_lo = max(xa, 2 * M + 1), xv_hi = min(xb, G.dim[0] - 2 * M - 1);
@@ -187,7 +192,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 #pragma unroll
     for (int k = 0; k < 2 * M + 1; ++k) txy[k] = txz[k] = 0;
     T vself = 0, wself = 0;                // V,W[t0] at plane xs-M (saved one iteration earlier)
-    const int ly = ty + M, lz = tz + M;    // coordinates inside the velocity tile
+    const int ly = ty + M, lz = tz + K::OFFZ;   // coordinates inside the velocity tile
     const int lo = ly * K::VZ + lz;
 
     // prefetch T[t0] of the first plane

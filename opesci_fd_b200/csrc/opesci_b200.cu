@@ -400,7 +400,7 @@ int setup_fused(Run &R)
         encode = (EncodeTiledFn)fn;
     }
     const int m = M.m;
-    const int VZ = 64 + 2 * m, VY = 16 + 2 * m;
+    const int VZ = m == 1 ? FusedCfg<1>::VZ : FusedCfg<2>::VZ, VY = 16 + 2 * m;
     for (int f = 0; f < 3; ++f) {
         cuuint64_t gdim[3] = {(cuuint64_t)p.dim[2], (cuuint64_t)p.dim[1], (cuuint64_t)p.dim[0] * p.nlevels};
         cuuint64_t gstride[2] = {(cuuint64_t)M.G.s[1] * 4, (cuuint64_t)M.G.s[0] * 4};
@@ -417,7 +417,7 @@ int setup_fused(Run &R)
     // warm-up of every chunk negligible
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
-    const int CZ = 64 - 2 * m, CY = 16 - 2 * m;
+    const int CZ = m == 1 ? FusedCfg<1>::CZ : FusedCfg<2>::CZ, CY = 16 - 2 * m;
     const long long tiles = (long long)((p.dim[2] - 2 * m + CZ - 1) / CZ) * ((p.dim[1] - 2 * m + CY - 1) / CY);
     const int nx = p.dim[0] - 2 * m;
     double best = -1.0;
