@@ -126,12 +126,15 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     constexpr int M = SO / 2;
     using K = FusedCfg<M>;
     typedef float T;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    // [field][slot] velocity tiles, then [field5][slot] stress tiles, then mbarriers
-    auto vtile = [&](int f, int slot) -> const T * { return (const T *)(smem + (size_t)(f * K::RD + slot) * K::VTILE); };
-    T *sring = (T *)(smem + (size_t)3 * K::RD * K::VTILE);
-    uint64_t *bars = (uint64_t *)(smem + (size_t)3 * K::RD * K::VTILE + (size_t)5 * K::SR * K::STILE);
+    constexpr int RD = K::RD;
+    constexpr int VT = K::VTILE / 4;      // floats per velocity tile
+    constexpr int ST = K::STILE / 4;      // floats per stress tile
+    // dynamic shared memory (no static __shared__ in this kernel, so the window starts 1024-B
+    // aligned): [3][RD] velocity tiles | [5][SR] stress tiles | mbarriers
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const T *vring = reinterpret_cast<const T *>(smem);
+    T *sring = reinterpret_cast<T *>(smem + (size_t)3 * RD * K::VTILE);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)3 * RD * K::VTILE + (size_t)5 * K::SR * K::STILE);
 
     const GridGeom &G = A.G;
     const int tid = threadIdx.x;
@@ -140,6 +143,8 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     const int xa = M + blockIdx.z * A.xchunk;
     const int xb = min(xa + A.xchunk, G.dim[0] - M);
     const int xs_begin = max(M, xa - M), xs_end = min(G.dim[0] - M, xb + M);
+    // plane p of U lives in slot (p - pbaseU) % RD, of V/W in slot (p - pbaseVW) % RD; with the
+    // x loop unrolled RD times every slot index below is a compile-time constant
     const int pbaseU = xs_begin - M, pbaseVW = xs_begin - M + 1;
     const int lastU = xs_end + M - 2, lastVW = xs_end + M - 1;
     const int c0 = blockIdx.x * K::CZ - K::OFFZ, c1 = blockIdx.y * K::CY - M;   // TMA box origin (may be negative)
@@ -147,26 +152,26 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     constexpr uint32_t TILE_BYTES = K::VZ * K::VY * 4;
 
     if (tid == 0) {
-        for (int i = 0; i < 3 * K::RD; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < 3 * RD; ++i) mbar_init(&bars[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int f, int plane, int pbase) {
-        const int slot = (plane - pbase) % K::RD;
-        uint64_t *bar = &bars[f * K::RD + slot];
-        mbar_arrive_expect_tx(bar, TILE_BYTES);
-        if (f == 0) tma_load_3d((void *)vtile(0, slot), &tmU, bar, c0, c1, lvl0 + plane);
-        else if (f == 1) tma_load_3d((void *)vtile(1, slot), &tmV, bar, c0, c1, lvl0 + plane);
-        else tma_load_3d((void *)vtile(2, slot), &tmW, bar, c0, c1, lvl0 + plane);
-    };
     if (tid == 0) {
-        for (int k = 0; k < K::RD; ++k) {
-            if (pbaseU + k <= lastU) issue(0, pbaseU + k, pbaseU);
-            if (pbaseVW + k <= lastVW) { issue(1, pbaseVW + k, pbaseVW); issue(2, pbaseVW + k, pbaseVW); }
+#pragma unroll
+        for (int k = 0; k < RD; ++k) {
+            if (pbaseU + k <= lastU) {
+                mbar_arrive_expect_tx(&bars[0 * RD + k], TILE_BYTES);
+                tma_load_3d((void *)(vring + (0 * RD + k) * VT), &tmU, &bars[0 * RD + k], c0, c1, lvl0 + pbaseU + k);
+            }
+            if (pbaseVW + k <= lastVW) {
+                mbar_arrive_expect_tx(&bars[1 * RD + k], TILE_BYTES);
+                tma_load_3d((void *)(vring + (1 * RD + k) * VT), &tmV, &bars[1 * RD + k], c0, c1, lvl0 + pbaseVW + k);
+                mbar_arrive_expect_tx(&bars[2 * RD + k], TILE_BYTES);
+                tma_load_3d((void *)(vring + (2 * RD + k) * VT), &tmW, &bars[2 * RD + k], c0, c1, lvl0 + pbaseVW + k);
+            }
         }
     }
-    int waitedU = pbaseU - 1, waitedVW = pbaseVW - 1;
 
     const bool inb = ye < G.dim[1] && ze < G.dim[2];
     const bool core = ty >= M && ty < M + K::CY && tz >= M && tz < M + K::CZ;
@@ -175,8 +180,10 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     const int xv_lo = max(xa, 2 * M + 1), xv_hi = min(xb, G.dim[0] - 2 * M - 1);
     const long long pyz = (long long)ye * G.s[1] + ze;
     const long long lv0 = (long long)A.t0 * G.level, lv1 = (long long)A.t1 * G.level;
-    const T *gT0[6];
-    T *gT1[6], *gV1[3];
+    const long long sx = G.s[0];
+    const T *__restrict__ gT0[6];
+    T *__restrict__ gT1[6];
+    T *__restrict__ gV1[3];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         gT0[k] = (const T *)A.F.f[F_TXX + k] + lv0 + pyz;
@@ -192,173 +199,195 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 #pragma unroll
     for (int k = 0; k < 2 * M + 1; ++k) txy[k] = txz[k] = 0;
     T vself = 0, wself = 0;                // V,W[t0] at plane xs-M (saved one iteration earlier)
-    const int ly = ty + M, lz = tz + K::OFFZ;   // coordinates inside the velocity tile
-    const int lo = ly * K::VZ + lz;
+    const int lo = (ty + M) * K::VZ + tz + K::OFFZ;   // this thread's element inside a velocity tile
+    const T *vlo = vring + lo;
+    T *slo = sring + ty * K::EZ + tz;
 
-    // prefetch T[t0] of the first plane
+    // T[t0] of the first plane
     T told[6];
+    long long px = (long long)xs_begin * sx;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) told[k] = inb ? gT0[k][(long long)xs_begin * G.s[0]] : (T)0;
+    for (int k = 0; k < 6; ++k) told[k] = inb ? gT0[k][px] : (T)0;
 
-    for (int xs = xs_begin; xs < xs_end; ++xs) {
-        // ---- wait for the newest planes of this iteration
-        while (waitedU < xs + M - 1) {
-            ++waitedU;
-            mbar_wait(&bars[0 * K::RD + (waitedU - pbaseU) % K::RD], ((waitedU - pbaseU) / K::RD) & 1);
-        }
-        while (waitedVW < xs + M) {
-            ++waitedVW;
-            const int s = (waitedVW - pbaseVW) % K::RD, par = ((waitedVW - pbaseVW) / K::RD) & 1;
-            mbar_wait(&bars[1 * K::RD + s], par);
-            mbar_wait(&bars[2 * K::RD + s], par);
-        }
-        // ---- gather operands of the six stress updates from the ring
-        T ux[2 * M], vx[2 * M], wx[2 * M];   // x-windows: U bwd (xs-M..xs+M-1), V,W fwd (xs-M+1..xs+M)
+    // planes of the first window (first use of their slots: phase parity 0)
 #pragma unroll
-        for (int j = 0; j < 2 * M; ++j) {
-            ux[j] = vtile(0, (xs - M + j - pbaseU) % K::RD)[lo];
-            vx[j] = vtile(1, (xs - M + 1 + j - pbaseVW) % K::RD)[lo];
-            wx[j] = vtile(2, (xs - M + 1 + j - pbaseVW) % K::RD)[lo];
-        }
-        const T *pu = vtile(0, (xs - pbaseU) % K::RD) + lo;
-        const T *pv = vtile(1, (xs - pbaseVW) % K::RD) + lo;
-        const T *pw = vtile(2, (xs - pbaseVW) % K::RD) + lo;
-        T vy_b[2 * M], wz_b[2 * M];          // backward windows in-plane (normal stresses)
-        T uy_f[2 * M], uz_f[2 * M], vz_f[2 * M], wy_f[2 * M];   // forward windows in-plane (shear stresses)
+    for (int k = 0; k < 2 * M - 1; ++k) {
+        mbar_wait(&bars[0 * RD + k], 0);
+        mbar_wait(&bars[1 * RD + k], 0);
+        mbar_wait(&bars[2 * RD + k], 0);
+    }
+
+    for (int xs0 = xs_begin, q = 0; xs0 < xs_end; xs0 += RD, ++q) {
 #pragma unroll
-        for (int j = 0; j < 2 * M; ++j) {
-            vy_b[j] = pv[(j - M) * K::VZ];
-            wz_b[j] = pw[(j - M)];
-            uy_f[j] = pu[(j - M + 1) * K::VZ];
-            uz_f[j] = pu[(j - M + 1)];
-            vz_f[j] = pv[(j - M + 1)];
-            wy_f[j] = pw[(j - M + 1) * K::VZ];
-        }
-        const T uself = ux[0];               // U[t0] at plane xs-M (velocity self term of this iteration)
-        const T vself_next = vx[0], wself_next = wx[0];   // V,W[t0] at plane xs-M+1
-        T tn[6];
-        if (ARITH == OPESCI_ARITH_REFERENCE) {
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                T acc = told[a];
-                bool first = false;
-                window_ref_arr<M, T, false>(acc, first, ux, A.C.sn[a][0]);
-                window_ref_arr<M, T, false>(acc, first, vy_b, A.C.sn[a][1]);
-                window_ref_arr<M, T, false>(acc, first, wz_b, A.C.sn[a][2]);
-                tn[a] = acc;
-            }
+        for (int r = 0; r < RD; ++r) {
+            const int xs = xs0 + r;
+            if (xs >= xs_end) break;
+            // ---- the newest planes of this iteration: relative plane index RD*q + r + 2M-1
             {
-                T acc = told[3]; bool first = false;   // Txy: D_y U, D_x V
-                window_ref_arr<M, T, true>(acc, first, uy_f, A.C.ss[0][0]);
-                window_ref_arr<M, T, true>(acc, first, vx, A.C.ss[0][1]);
-                tn[3] = acc;
+                constexpr int rel = 0;   // placeholder to keep the block scoped
+                (void)rel;
+                const int slot = (r + 2 * M - 1) % RD;
+                const uint32_t par = (uint32_t)(q + (r + 2 * M - 1) / RD) & 1u;
+                mbar_wait(&bars[0 * RD + slot], par);
+                mbar_wait(&bars[1 * RD + slot], par);
+                mbar_wait(&bars[2 * RD + slot], par);
             }
-            {
-                T acc = told[4]; bool first = false;   // Tyz: D_z V, D_y W
-                window_ref_arr<M, T, true>(acc, first, vz_f, A.C.ss[1][0]);
-                window_ref_arr<M, T, true>(acc, first, wy_f, A.C.ss[1][1]);
-                tn[4] = acc;
-            }
-            {
-                T acc = told[5]; bool first = false;   // Txz: D_z U, D_x W
-                window_ref_arr<M, T, true>(acc, first, uz_f, A.C.ss[2][0]);
-                window_ref_arr<M, T, true>(acc, first, wx, A.C.ss[2][1]);
-                tn[5] = acc;
-            }
-        } else {
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-                tn[a] = told[a] + (window_fast_arr<M, T, false>(ux, A.C.sn[a][0]) + window_fast_arr<M, T, false>(vy_b, A.C.sn[a][1]) +
-                                   window_fast_arr<M, T, false>(wz_b, A.C.sn[a][2]));
-            tn[3] = told[3] + (window_fast_arr<M, T, true>(uy_f, A.C.ss[0][0]) + window_fast_arr<M, T, true>(vx, A.C.ss[0][1]));
-            tn[4] = told[4] + (window_fast_arr<M, T, true>(vz_f, A.C.ss[1][0]) + window_fast_arr<M, T, true>(wy_f, A.C.ss[1][1]));
-            tn[5] = told[5] + (window_fast_arr<M, T, true>(uz_f, A.C.ss[2][0]) + window_fast_arr<M, T, true>(wx, A.C.ss[2][1]));
-        }
-        // ---- store the new stresses (owned tile, owned planes), prefetch next T[t0]
-        const long long px = (long long)xs * G.s[0];
-        if (st_yz && xs >= xa && xs < xb) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) gT1[k][px] = tn[k];
-        }
-        if (xs + 1 < xs_end) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) told[k] = inb ? gT0[k][px + G.s[0]] : (T)0;
-        }
-        // ---- shift the register windows, publish the in-plane operands
-#pragma unroll
-        for (int k = 0; k < 2 * M - 1; ++k) txx[k] = txx[k + 1];
-        txx[2 * M - 1] = tn[0];
-#pragma unroll
-        for (int k = 0; k < 2 * M; ++k) { txy[k] = txy[k + 1]; txz[k] = txz[k + 1]; }
-        txy[2 * M] = tn[3];
-        txz[2 * M] = tn[5];
-        {
-            const int slot = xs & (K::SR - 1);
-            T *s = sring + (size_t)slot * (K::STILE / 4) + ty * K::EZ + tz;
-            s[0 * K::SR * (K::STILE / 4)] = tn[3];   // Txy
-            s[1 * K::SR * (K::STILE / 4)] = tn[5];   // Txz
-            s[2 * K::SR * (K::STILE / 4)] = tn[1];   // Tyy
-            s[3 * K::SR * (K::STILE / 4)] = tn[4];   // Tyz
-            s[4 * K::SR * (K::STILE / 4)] = tn[2];   // Tzz
-        }
-        __syncthreads();
-        // ---- the oldest planes are dead: refill their slots
-        if (tid == 0) {
-            const int pU = xs - M + K::RD, pVW = xs - M + 1 + K::RD;
-            if (pU <= lastU) issue(0, pU, pbaseU);
-            if (pVW <= lastVW) { issue(1, pVW, pbaseVW); issue(2, pVW, pbaseVW); }
-        }
-        // ---- velocities of plane xv = xs - M from the new stresses xv-M .. xv+M
-        const int xv = xs - M;
-        if (vf_yz && xv >= xv_lo && xv < xv_hi) {
-            const int slot = xv & (K::SR - 1);
-            const T *s = sring + (size_t)slot * (K::STILE / 4) + ty * K::EZ + tz;
-            const T *sxy = s, *sxz = s + 1 * K::SR * (K::STILE / 4), *syy = s + 2 * K::SR * (K::STILE / 4),
-                    *syz = s + 3 * K::SR * (K::STILE / 4), *szz = s + 4 * K::SR * (K::STILE / 4);
-            T xy_yb[2 * M], xz_zb[2 * M], yy_yf[2 * M], yz_zb[2 * M], yz_yb[2 * M], zz_zf[2 * M];
+            // ---- gather the operands of the six stress updates (all offsets are immediates)
+            T ux[2 * M], vx[2 * M], wx[2 * M];   // x-windows: U bwd (xs-M..xs+M-1), V,W fwd (xs-M+1..xs+M)
 #pragma unroll
             for (int j = 0; j < 2 * M; ++j) {
-                xy_yb[j] = sxy[(j - M) * K::EZ];
-                xz_zb[j] = sxz[(j - M)];
-                yy_yf[j] = syy[(j - M + 1) * K::EZ];
-                yz_zb[j] = syz[(j - M)];
-                yz_yb[j] = syz[(j - M) * K::EZ];
-                zz_zf[j] = szz[(j - M + 1)];
+                const int slot = (r + j) % RD;
+                ux[j] = vlo[(0 * RD + slot) * VT];
+                vx[j] = vlo[(1 * RD + slot) * VT];
+                wx[j] = vlo[(2 * RD + slot) * VT];
             }
-            // x-windows from registers: Txx fwd = planes xv-M+1..xv+M = txx[0..2M-1];
-            // Txy, Txz bwd = planes xv-M..xv+M-1 = txy[0..2M-1]
-            T un, vn, wn;
+            // plane xs: U is window entry M (slot r+M), V/W window entry M-1 (slot r+M-1)
+            const T *pu = vlo + (0 * RD + (r + M) % RD) * VT;
+            const T *pv = vlo + (1 * RD + (r + M - 1) % RD) * VT;
+            const T *pw = vlo + (2 * RD + (r + M - 1) % RD) * VT;
+            T vy_b[2 * M], wz_b[2 * M];          // backward windows in-plane (normal stresses)
+            T uy_f[2 * M], uz_f[2 * M], vz_f[2 * M], wy_f[2 * M];   // forward windows in-plane (shear stresses)
+#pragma unroll
+            for (int j = 0; j < 2 * M; ++j) {
+                vy_b[j] = pv[(j - M) * K::VZ];
+                wz_b[j] = pw[(j - M)];
+                uy_f[j] = pu[(j - M + 1) * K::VZ];
+                uz_f[j] = pu[(j - M + 1)];
+                vz_f[j] = pv[(j - M + 1)];
+                wy_f[j] = pw[(j - M + 1) * K::VZ];
+            }
+            const T uself = ux[0];               // U[t0] at plane xs-M (velocity self term of this iteration)
+            const T vself_next = vx[0], wself_next = wx[0];   // V,W[t0] at plane xs-M+1
+            T tn[6];
             if (ARITH == OPESCI_ARITH_REFERENCE) {
-                T acc = 0; bool first = true;
-                window_ref_arr<M, T, true>(acc, first, txx, A.C.v[0][0]);
-                window_ref_arr<M, T, false>(acc, first, xy_yb, A.C.v[0][1]);
-                window_ref_arr<M, T, false>(acc, first, xz_zb, A.C.v[0][2]);
-                un = add_rn<T>(acc, uself);
-                acc = 0; first = true;
-                window_ref_arr<M, T, false>(acc, first, txy, A.C.v[1][0]);
-                window_ref_arr<M, T, true>(acc, first, yy_yf, A.C.v[1][1]);
-                window_ref_arr<M, T, false>(acc, first, yz_zb, A.C.v[1][2]);
-                vn = add_rn<T>(acc, vself);
-                acc = 0; first = true;
-                window_ref_arr<M, T, false>(acc, first, txz, A.C.v[2][0]);
-                window_ref_arr<M, T, false>(acc, first, yz_yb, A.C.v[2][1]);
-                window_ref_arr<M, T, true>(acc, first, zz_zf, A.C.v[2][2]);
-                wn = add_rn<T>(acc, wself);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    T acc = told[a];
+                    bool first = false;
+                    window_ref_arr<M, T, false>(acc, first, ux, A.C.sn[a][0]);
+                    window_ref_arr<M, T, false>(acc, first, vy_b, A.C.sn[a][1]);
+                    window_ref_arr<M, T, false>(acc, first, wz_b, A.C.sn[a][2]);
+                    tn[a] = acc;
+                }
+                {
+                    T acc = told[3]; bool first = false;   // Txy: D_y U, D_x V
+                    window_ref_arr<M, T, true>(acc, first, uy_f, A.C.ss[0][0]);
+                    window_ref_arr<M, T, true>(acc, first, vx, A.C.ss[0][1]);
+                    tn[3] = acc;
+                }
+                {
+                    T acc = told[4]; bool first = false;   // Tyz: D_z V, D_y W
+                    window_ref_arr<M, T, true>(acc, first, vz_f, A.C.ss[1][0]);
+                    window_ref_arr<M, T, true>(acc, first, wy_f, A.C.ss[1][1]);
+                    tn[4] = acc;
+                }
+                {
+                    T acc = told[5]; bool first = false;   // Txz: D_z U, D_x W
+                    window_ref_arr<M, T, true>(acc, first, uz_f, A.C.ss[2][0]);
+                    window_ref_arr<M, T, true>(acc, first, wx, A.C.ss[2][1]);
+                    tn[5] = acc;
+                }
             } else {
-                un = uself + (window_fast_arr<M, T, true>(txx, A.C.v[0][0]) + window_fast_arr<M, T, false>(xy_yb, A.C.v[0][1]) +
-                              window_fast_arr<M, T, false>(xz_zb, A.C.v[0][2]));
-                vn = vself + (window_fast_arr<M, T, false>(txy, A.C.v[1][0]) + window_fast_arr<M, T, true>(yy_yf, A.C.v[1][1]) +
-                              window_fast_arr<M, T, false>(yz_zb, A.C.v[1][2]));
-                wn = wself + (window_fast_arr<M, T, false>(txz, A.C.v[2][0]) + window_fast_arr<M, T, false>(yz_yb, A.C.v[2][1]) +
-                              window_fast_arr<M, T, true>(zz_zf, A.C.v[2][2]));
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                    tn[a] = told[a] + (window_fast_arr<M, T, false>(ux, A.C.sn[a][0]) + window_fast_arr<M, T, false>(vy_b, A.C.sn[a][1]) +
+                                       window_fast_arr<M, T, false>(wz_b, A.C.sn[a][2]));
+                tn[3] = told[3] + (window_fast_arr<M, T, true>(uy_f, A.C.ss[0][0]) + window_fast_arr<M, T, true>(vx, A.C.ss[0][1]));
+                tn[4] = told[4] + (window_fast_arr<M, T, true>(vz_f, A.C.ss[1][0]) + window_fast_arr<M, T, true>(wy_f, A.C.ss[1][1]));
+                tn[5] = told[5] + (window_fast_arr<M, T, true>(uz_f, A.C.ss[2][0]) + window_fast_arr<M, T, true>(wx, A.C.ss[2][1]));
             }
-            const long long pxv = (long long)xv * G.s[0];
-            gV1[0][pxv] = un;
-            gV1[1][pxv] = vn;
-            gV1[2][pxv] = wn;
+            // ---- store the new stresses (owned tile, owned planes), prefetch next T[t0]
+            if (st_yz && xs >= xa && xs < xb) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) gT1[k][px] = tn[k];
+            }
+            px += sx;
+            if (xs + 1 < xs_end) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) told[k] = inb ? gT0[k][px] : (T)0;
+            }
+            // ---- shift the register windows, publish the in-plane operands
+#pragma unroll
+            for (int k = 0; k < 2 * M - 1; ++k) txx[k] = txx[k + 1];
+            txx[2 * M - 1] = tn[0];
+#pragma unroll
+            for (int k = 0; k < 2 * M; ++k) { txy[k] = txy[k + 1]; txz[k] = txz[k + 1]; }
+            txy[2 * M] = tn[3];
+            txz[2 * M] = tn[5];
+            {
+                T *s = slo + (xs & (K::SR - 1)) * ST;
+                s[0 * K::SR * ST] = tn[3];   // Txy
+                s[1 * K::SR * ST] = tn[5];   // Txz
+                s[2 * K::SR * ST] = tn[1];   // Tyy
+                s[3 * K::SR * ST] = tn[4];   // Tyz
+                s[4 * K::SR * ST] = tn[2];   // Tzz
+            }
+            __syncthreads();
+            // ---- the oldest planes (window entry 0, slot r) are dead: refill their slots
+            if (tid == 0) {
+                const int pU = xs - M + RD, pVW = xs - M + 1 + RD;
+                if (pU <= lastU) {
+                    mbar_arrive_expect_tx(&bars[0 * RD + r], TILE_BYTES);
+                    tma_load_3d((void *)(vring + (0 * RD + r) * VT), &tmU, &bars[0 * RD + r], c0, c1, lvl0 + pU);
+                }
+                if (pVW <= lastVW) {
+                    mbar_arrive_expect_tx(&bars[1 * RD + r], TILE_BYTES);
+                    tma_load_3d((void *)(vring + (1 * RD + r) * VT), &tmV, &bars[1 * RD + r], c0, c1, lvl0 + pVW);
+                    mbar_arrive_expect_tx(&bars[2 * RD + r], TILE_BYTES);
+                    tma_load_3d((void *)(vring + (2 * RD + r) * VT), &tmW, &bars[2 * RD + r], c0, c1, lvl0 + pVW);
+                }
+            }
+            // ---- velocities of plane xv = xs - M from the new stresses xv-M .. xv+M
+            const int xv = xs - M;
+            if (vf_yz && xv >= xv_lo && xv < xv_hi) {
+                const T *s = slo + (xv & (K::SR - 1)) * ST;
+                const T *sxy = s, *sxz = s + 1 * K::SR * ST, *syy = s + 2 * K::SR * ST, *syz = s + 3 * K::SR * ST,
+                        *szz = s + 4 * K::SR * ST;
+                T xy_yb[2 * M], xz_zb[2 * M], yy_yf[2 * M], yz_zb[2 * M], yz_yb[2 * M], zz_zf[2 * M];
+#pragma unroll
+                for (int j = 0; j < 2 * M; ++j) {
+                    xy_yb[j] = sxy[(j - M) * K::EZ];
+                    xz_zb[j] = sxz[(j - M)];
+                    yy_yf[j] = syy[(j - M + 1) * K::EZ];
+                    yz_zb[j] = syz[(j - M)];
+                    yz_yb[j] = syz[(j - M) * K::EZ];
+                    zz_zf[j] = szz[(j - M + 1)];
+                }
+                // x-windows from registers: Txx fwd = planes xv-M+1..xv+M = txx[0..2M-1];
+                // Txy, Txz bwd = planes xv-M..xv+M-1 = txy[0..2M-1]
+                T un, vn, wn;
+                if (ARITH == OPESCI_ARITH_REFERENCE) {
+                    T acc = 0; bool first = true;
+                    window_ref_arr<M, T, true>(acc, first, txx, A.C.v[0][0]);
+                    window_ref_arr<M, T, false>(acc, first, xy_yb, A.C.v[0][1]);
+                    window_ref_arr<M, T, false>(acc, first, xz_zb, A.C.v[0][2]);
+                    un = add_rn<T>(acc, uself);
+                    acc = 0; first = true;
+                    window_ref_arr<M, T, false>(acc, first, txy, A.C.v[1][0]);
+                    window_ref_arr<M, T, true>(acc, first, yy_yf, A.C.v[1][1]);
+                    window_ref_arr<M, T, false>(acc, first, yz_zb, A.C.v[1][2]);
+                    vn = add_rn<T>(acc, vself);
+                    acc = 0; first = true;
+                    window_ref_arr<M, T, false>(acc, first, txz, A.C.v[2][0]);
+                    window_ref_arr<M, T, false>(acc, first, yz_yb, A.C.v[2][1]);
+                    window_ref_arr<M, T, true>(acc, first, zz_zf, A.C.v[2][2]);
+                    wn = add_rn<T>(acc, wself);
+                } else {
+                    un = uself + (window_fast_arr<M, T, true>(txx, A.C.v[0][0]) + window_fast_arr<M, T, false>(xy_yb, A.C.v[0][1]) +
+                                  window_fast_arr<M, T, false>(xz_zb, A.C.v[0][2]));
+                    vn = vself + (window_fast_arr<M, T, false>(txy, A.C.v[1][0]) + window_fast_arr<M, T, true>(yy_yf, A.C.v[1][1]) +
+                                  window_fast_arr<M, T, false>(yz_zb, A.C.v[1][2]));
+                    wn = wself + (window_fast_arr<M, T, false>(txz, A.C.v[2][0]) + window_fast_arr<M, T, false>(yz_yb, A.C.v[2][1]) +
+                                  window_fast_arr<M, T, true>(zz_zf, A.C.v[2][2]));
+                }
+                const long long pxv = px - (long long)(M + 1) * sx;   // px already points at plane xs+1
+                gV1[0][pxv] = un;
+                gV1[1][pxv] = vn;
+                gV1[2][pxv] = wn;
+            }
+            vself = vself_next;
+            wself = wself_next;
         }
-        vself = vself_next;
-        wself = wself_next;
     }
 }
 
