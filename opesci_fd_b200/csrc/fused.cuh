@@ -432,4 +432,60 @@ velocity_box(FieldPtrs F, GridGeom G, StaggeredCoefs C, int t0, int t1, Range3 R
     }
 }
 
+// All six shell slabs in one launch: blockIdx.x is a flat block index over the boxes.
+struct ShellBoxes {
+    Range3 r[6];
+    int zwide[6];        // 1: 64 x 4 threads (z x y), 0: 4 x 64
+    int nbz[6], nby[6];  // blocks along z and y
+    int start[7];        // prefix sums of the block counts
+};
+template <int SO, typename T, int ARITH>
+__global__ void __launch_bounds__(256)
+velocity_shell_kernel(FieldPtrs F, GridGeom G, StaggeredCoefs C, int t0, int t1, const __grid_constant__ ShellBoxes B)
+{
+    constexpr int M = SO / 2;
+    int b = 0;
+#pragma unroll
+    for (int k = 1; k < 6; ++k)
+        if ((int)blockIdx.x >= B.start[k]) b = k;
+    const Range3 &R = B.r[b];
+    int rem = blockIdx.x - B.start[b];
+    const int bz = rem % B.nbz[b];
+    rem /= B.nbz[b];
+    const int by = rem % B.nby[b], bx = rem / B.nby[b];
+    const int tw = B.zwide[b] ? 64 : 4, th = 256 / tw;
+    const int z = R.lo[2] + bz * tw + (int)(threadIdx.x % tw);
+    const int y = R.lo[1] + by * th + (int)(threadIdx.x / tw);
+    const int x = R.lo[0] + bx;
+    if (z >= R.hi[2] || y >= R.hi[1]) return;
+    const long long p = (long long)x * G.s[0] + (long long)y * G.s[1] + z;
+    const long long r = (long long)t0 * G.level + p, w = (long long)t1 * G.level + p;
+    const long long st[3] = {G.s[0], G.s[1], 1};
+    const int opnd[3][3] = {{F_TXX, F_TXY, F_TXZ}, {F_TXY, F_TYY, F_TYZ}, {F_TXZ, F_TYZ, F_TZZ}};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        T *Va = (T *)F.f[F_U + a];
+        if (ARITH == OPESCI_ARITH_REFERENCE) {
+            T acc = 0;
+            bool first = true;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const T *g = (const T *)F.f[opnd[a][d]] + w;
+                if (d == a) window_ref<M, T, true>(acc, first, g, st[d], C.v[a][d]);
+                else window_ref<M, T, false>(acc, first, g, st[d], C.v[a][d]);
+            }
+            Va[w] = add_rn<T>(acc, Va[r]);
+        } else {
+            T acc = 0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const T *g = (const T *)F.f[opnd[a][d]] + w;
+                acc += (d == a) ? window_fast<M, T, true>(g, st[d], C.v[a][d])
+                                : window_fast<M, T, false>(g, st[d], C.v[a][d]);
+            }
+            Va[w] = Va[r] + acc;
+        }
+    }
+}
+
 }  // namespace opesci

@@ -296,6 +296,71 @@ __global__ void face_mirror(T *__restrict__ A /* level base */, GridGeom G, Mirr
     }
 }
 
+
+// ---- batched ghost-cell loops -----------------------------------------------------------
+// The reference runs its 48 (so=4) / 36 ghost loops one after the other, each an `omp for`
+// with a barrier.  Loops that cannot see each other's writes (different output field, or the
+// low / high side of one face pair) are launched together: blockIdx.z selects the loop.
+struct FaceLoop {
+    int kind;           // 0: plane assignments (MirrorOps)   1: emitted sum (DevEq)
+    int d, n;           // face normal axis; target plane (equation loops)
+    int lo, hi1, hi2;   // ranges [lo,hi1) x [lo,hi2) on the other two axes (e1 < e2)
+    int field, level;   // mirror loops: array and time level
+    int lv0, lv1;       // equation loops: time levels of slots 0 / 1
+    MirrorOps ops;
+    DevEq eq;
+};
+#define OPESCI_MAX_BATCH 12
+struct FaceBatch {
+    int count;
+    int start[OPESCI_MAX_BATCH + 1];   // prefix sums of the per-loop block counts (flat blockIdx.x)
+    int nbx[OPESCI_MAX_BATCH];         // blocks along e2 of each loop
+    FaceLoop loop[OPESCI_MAX_BATCH];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+face_batch(FieldPtrs F, GridGeom G, const __grid_constant__ FaceBatch B)
+{
+    int li = 0;
+    for (int k = 1; k < B.count; ++k)
+        if ((int)blockIdx.x >= B.start[k]) li = k;
+    const FaceLoop &L = B.loop[li];
+    const int rem = blockIdx.x - B.start[li];
+    const int bx = rem % B.nbx[li], by = rem / B.nbx[li];
+    const int d = L.d;
+    const int e1 = (d == 0) ? 1 : 0, e2 = (d == 2) ? 1 : 2;
+    // threads run along e2 (contiguous z) except on z-faces, where 8 x 32 tiles keep a little locality
+    const int w = (d == 2) ? 8 : 128, h = 256 / w;
+    const int j = L.lo + bx * w + (int)(threadIdx.x % w);
+    const int i = L.lo + by * h + (int)(threadIdx.x / w);
+    if (i >= L.hi1 || j >= L.hi2) return;
+    const long long q = (long long)i * G.s[e1] + (long long)j * G.s[e2];
+    if (L.kind == 0) {
+        T *A = (T *)F.f[L.field] + (long long)L.level * G.level;
+        for (int k = 0; k < L.ops.count; ++k) {
+            const T v = L.ops.src[k] < 0 ? (T)0 : -A[q + (long long)L.ops.src[k] * G.s[d]];
+            A[q + (long long)L.ops.dst[k] * G.s[d]] = v;
+        }
+    } else {
+        const long long p = q + (long long)L.n * G.s[d];
+        const long long lv[2] = {(long long)L.lv0 * G.level, (long long)L.lv1 * G.level};
+        T acc = 0;
+        bool first = true;
+        for (int k = 0; k < L.eq.nterm; ++k) {
+            const DevTerm &t = L.eq.term[k];
+            const T g = ((const T *)F.f[t.field])[lv[t.level] + p + t.off];
+            T v;
+            if (t.kind == TERM_MUL) v = mul_rn<T>((T)t.coef, g);
+            else if (t.kind == TERM_PLUS) v = g;
+            else v = -g;
+            acc = first ? v : add_rn<T>(acc, v);
+            first = false;
+        }
+        ((T *)F.f[L.eq.out])[lv[L.eq.out_level] + p] = acc;
+    }
+}
+
 // ------------------------------------------------------------------ analytic programs
 struct DevProgram {
     int n_instr, n_tables;

@@ -236,17 +236,75 @@ struct Stepper {
         check();
     }
 
-    // stress ghost loops in the reference's order (opesci/staggeredgrid.py:754-813)
+    // ---- batched ghost loops: loops that cannot observe each other run in one launch
+    template <typename T> void launch_batch(FaceBatch &B)
+    {
+        if (B.count == 0) return;
+        const Model &M = R.M;
+        int total = 0;
+        for (int k = 0; k < B.count; ++k) {
+            const FaceLoop &L = B.loop[k];
+            const int w = L.d == 2 ? 8 : 128, h = 256 / w;
+            B.nbx[k] = (L.hi2 - L.lo + w - 1) / w;
+            B.start[k] = total;
+            total += B.nbx[k] * ((L.hi1 - L.lo + h - 1) / h);
+        }
+        B.start[B.count] = total;
+        face_batch<T><<<total, 256, 0, st>>>(ptrs(), M.G, B);
+        check();
+    }
+    bool add_mirror(FaceBatch &B, int field, int level, int d, const MirrorOps &ops, int lo, int himargin) const
+    {
+        const Model &M = R.M;
+        const int e1 = d == 0 ? 1 : 0, e2 = d == 2 ? 1 : 2;
+        FaceLoop &L = B.loop[B.count];
+        L.kind = 0; L.d = d; L.n = 0; L.lo = lo; L.hi1 = M.G.dim[e1] - himargin; L.hi2 = M.G.dim[e2] - himargin;
+        L.field = field; L.level = level; L.lv0 = L.lv1 = 0; L.ops = ops;
+        if (L.hi1 <= lo || L.hi2 <= lo) return false;
+        ++B.count;
+        return true;
+    }
+    bool add_equation(FaceBatch &B, const DevEq &eq, int lv0, int lv1, int d, int n, int lo, int himargin) const
+    {
+        const Model &M = R.M;
+        const int e1 = d == 0 ? 1 : 0, e2 = d == 2 ? 1 : 2;
+        FaceLoop &L = B.loop[B.count];
+        L.kind = 1; L.d = d; L.n = n; L.lo = lo; L.hi1 = M.G.dim[e1] - himargin; L.hi2 = M.G.dim[e2] - himargin;
+        L.field = 0; L.level = 0; L.lv0 = lv0; L.lv1 = lv1; L.eq = eq; L.ops.count = 0;
+        if (L.hi1 <= lo || L.hi2 <= lo) return false;
+        ++B.count;
+        return true;
+    }
+    // low and high side of one face pair never touch the same cells once the grid is this large
+    bool sides_independent() const
+    {
+        const Model &M = R.M;
+        for (int d = 0; d < 3; ++d)
+            if (M.G.dim[d] < 4 * M.m + 6) return false;
+        return true;
+    }
+
+    // stress ghost loops (opesci/staggeredgrid.py:754-813).  The reference's order is field by
+    // field (Txx,Tyy,Tzz,Txy,Tyz,Txz), face axis by face axis, low side then high side.  Loops of
+    // different fields write different arrays and read only level-t0 data or their own array, so
+    // the k-th loop of every field runs in launch k; within a field the order is kept.
     template <typename T> void stress_bc(int t0, int t1, bool init)
     {
         const Model &M = R.M;
         const int m = M.m;
         static const int ORDER[6] = {F_TXX, F_TYY, F_TZZ, F_TXY, F_TYZ, F_TXZ};
         static const int SH_A[3] = {0, 1, 0}, SH_B[3] = {1, 2, 2};
+        const bool pair = sides_independent();
+        // sequence of loops per field
+        FaceLoop seq[6][6];
+        int nseq[6] = {0, 0, 0, 0, 0, 0};
+        FaceBatch tmp;
         for (int fi = 0; fi < 6; ++fi)
             for (int d = 0; d < 3; ++d) {
                 const int b_lo = m, b_hi = M.G.dim[d] - m - 1;
                 for (int side = 0; side < 2; ++side) {
+                    tmp.count = 0;
+                    bool ok = false;
                     if (fi < 3 && fi == d) {
                         // own-axis normal stress (opesci/fields.py:355-381), ranges [0,dim)
                         MirrorOps ops;
@@ -254,12 +312,12 @@ struct Stepper {
                         const int b = side == 0 ? b_lo : b_hi, dir = side == 0 ? -1 : 1;
                         ops.dst[ops.count] = b; ops.src[ops.count++] = -1;
                         for (int k = 1; k <= m - 1; ++k) { ops.dst[ops.count] = b + dir * k; ops.src[ops.count++] = b - dir * k; }
-                        mirror<T>(ORDER[fi], t1, d, ops, 0, 0);
+                        ok = add_mirror(tmp, ORDER[fi], t1, d, ops, 0, 0);
                     } else if (fi < 3) {
                         // Levander recompute of the other normal stresses on this face from level t0
                         // (opesci/fields.py:313-353; not in the initial pass, staggeredgrid.py:771-773)
                         if (M.p.free_surface != 1 || init) continue;
-                        equation<T>(M.lev_stress_eq[d][fi], t0, t1, d, side == 0 ? b_lo : b_hi, m + 1, m + 1);
+                        ok = add_equation(tmp, M.lev_stress_eq[d][fi], t0, t1, d, side == 0 ? b_lo : b_hi, m + 1, m + 1);
                     } else {
                         const int a = SH_A[fi - 3], bb = SH_B[fi - 3];
                         if (d != a && d != bb) continue;
@@ -270,22 +328,38 @@ struct Stepper {
                             if (side == 0) { ops.dst[ops.count] = m - 1 - j; ops.src[ops.count++] = m + j; }
                             else { ops.dst[ops.count] = b_hi + j; ops.src[ops.count++] = b_hi - 1 - j; }
                         }
-                        mirror<T>(ORDER[fi], t1, d, ops, 0, 0);
+                        ok = add_mirror(tmp, ORDER[fi], t1, d, ops, 0, 0);
                     }
+                    if (ok) seq[fi][nseq[fi]++] = tmp.loop[0];
                 }
             }
+        const int stride = pair ? 2 : 1;   // low + high side of a face pair together
+        for (int k = 0; k < 6; k += stride) {
+            FaceBatch B;
+            B.count = 0;
+            for (int fi = 0; fi < 6; ++fi)
+                for (int j = k; j < k + stride && j < nseq[fi]; ++j) B.loop[B.count++] = seq[fi][j];
+            launch_batch<T>(B);
+        }
     }
 
-    // velocity ghost loops in the reference's order (opesci/staggeredgrid.py:815-864)
+    // velocity ghost loops (opesci/staggeredgrid.py:815-864): per face axis d the component
+    // staggered along d first (both sides), then the two tangential components, which read the
+    // freshly written normal ghosts but not each other.  Robertsson loops only write zeros.
     template <typename T> void velocity_bc(int t1)
     {
         const Model &M = R.M;
         const int m = M.m;
+        const bool pair = sides_independent();
+        FaceBatch robertsson;
+        robertsson.count = 0;
         for (int d = 0; d < 3; ++d) {
             int seq[3];
             seq[0] = d;
             for (int k = 0, n = 1; k < 3; ++k)
                 if (k != d) seq[n++] = k;
+            FaceBatch stage[2];
+            stage[0].count = stage[1].count = 0;
             for (int si = 0; si < 3; ++si) {
                 const int a = seq[si];
                 for (int side = 0; side < 2; ++side) {
@@ -294,7 +368,9 @@ struct Stepper {
                         if (a == d) n = side == 0 ? m - 1 : M.G.dim[d] - m - 1;
                         else n = side == 0 ? m - 1 : M.G.dim[d] - m;
                         // every operand and the result live on level t1 (slot 0 of the equation)
-                        equation<T>(M.lev_vel_eq[d][a][side], t1, t1, d, n, 1, 1);
+                        FaceBatch &B = stage[si == 0 ? 0 : 1];
+                        add_equation(B, M.lev_vel_eq[d][a][side], t1, t1, d, n, 1, 1);
+                        if (!pair) { launch_batch<T>(B); B.count = 0; }
                     } else if (M.p.free_surface == 2) {
                         // Robertsson: m ghost layers := 0 (opesci/fields.py:243-259)
                         MirrorOps ops;
@@ -305,11 +381,14 @@ struct Stepper {
                             else n = (a == d ? M.G.dim[d] - m - 1 : M.G.dim[d] - m) + j;
                             ops.dst[ops.count] = n; ops.src[ops.count++] = -1;
                         }
-                        mirror<T>(VEL_OF_AXIS[a], t1, d, ops, 1, 1);
+                        add_mirror(robertsson, VEL_OF_AXIS[a], t1, d, ops, 1, 1);
+                        if (robertsson.count == OPESCI_MAX_BATCH) { launch_batch<T>(robertsson); robertsson.count = 0; }
                     }
                 }
             }
+            if (pair) { launch_batch<T>(stage[0]); launch_batch<T>(stage[1]); }
         }
+        launch_batch<T>(robertsson);
     }
 
     // fused stress+velocity launch (fused.cuh); only instantiated for so <= 4, fp32
@@ -326,27 +405,40 @@ struct Stepper {
             check();
         }
     }
-    // velocity update of the shell the fused kernel leaves out: interior minus [2m+1, dim-2m-1)^3
+    // velocity update of the shell the fused kernel leaves out: interior minus [2m+1, dim-2m-1)^3,
+    // six disjoint slabs in one launch
     template <int SO, typename T, int ARITH> void velocity_shell(int t0, int t1)
     {
-        const Model &Md = R.M;
-        const int m = Md.m;
-        int lo[3], hi[3], ilo[3], ihi[3];
-        for (int d = 0; d < 3; ++d) { lo[d] = m; hi[d] = Md.G.dim[d] - m; ilo[d] = 2 * m + 1; ihi[d] = Md.G.dim[d] - 2 * m - 1; }
-        for (int d = 0; d < 3; ++d)
-            for (int side = 0; side < 2; ++side) {
-                Range3 rg;
-                for (int e = 0; e < 3; ++e) {
-                    if (e < d) { rg.lo[e] = ilo[e]; rg.hi[e] = ihi[e]; }     // already covered by earlier slabs
-                    else if (e == d) { rg.lo[e] = side == 0 ? lo[e] : ihi[e]; rg.hi[e] = side == 0 ? ilo[e] : hi[e]; }
-                    else { rg.lo[e] = lo[e]; rg.hi[e] = hi[e]; }
+        if constexpr (SO <= 4 && sizeof(T) == 4) {
+            const Model &Md = R.M;
+            const int m = Md.m;
+            int lo[3], hi[3], ilo[3], ihi[3];
+            for (int d = 0; d < 3; ++d) { lo[d] = m; hi[d] = Md.G.dim[d] - m; ilo[d] = 2 * m + 1; ihi[d] = Md.G.dim[d] - 2 * m - 1; }
+            ShellBoxes B;
+            int nb = 0, total = 0;
+            for (int d = 0; d < 3; ++d)
+                for (int side = 0; side < 2; ++side) {
+                    Range3 rg;
+                    for (int e = 0; e < 3; ++e) {
+                        if (e < d) { rg.lo[e] = ilo[e]; rg.hi[e] = ihi[e]; }     // already covered by earlier slabs
+                        else if (e == d) { rg.lo[e] = side == 0 ? lo[e] : ihi[e]; rg.hi[e] = side == 0 ? ilo[e] : hi[e]; }
+                        else { rg.lo[e] = lo[e]; rg.hi[e] = hi[e]; }
+                    }
+                    B.r[nb] = rg;
+                    B.zwide[nb] = d == 2 ? 0 : 1;
+                    const int tw = d == 2 ? 4 : 64, th = 256 / tw;
+                    const int nz = rg.hi[2] - rg.lo[2], ny = rg.hi[1] - rg.lo[1], nx = rg.hi[0] - rg.lo[0];
+                    B.nbz[nb] = nz > 0 ? (nz + tw - 1) / tw : 1;
+                    B.nby[nb] = ny > 0 ? (ny + th - 1) / th : 1;
+                    B.start[nb] = total;
+                    total += (nz > 0 && ny > 0 && nx > 0) ? B.nbz[nb] * B.nby[nb] * nx : 0;
+                    ++nb;
                 }
-                if (rg.hi[0] <= rg.lo[0] || rg.hi[1] <= rg.lo[1] || rg.hi[2] <= rg.lo[2]) continue;
-                dim3 blk = d == 2 ? dim3(4, 64) : dim3(64, 4);
-                dim3 grid((rg.hi[2] - rg.lo[2] + blk.x - 1) / blk.x, (rg.hi[1] - rg.lo[1] + blk.y - 1) / blk.y, rg.hi[0] - rg.lo[0]);
-                velocity_box<SO, T, ARITH><<<grid, blk, 0, st>>>(ptrs(), Md.G, Md.sc, t0, t1, rg);
-                check();
-            }
+            B.start[6] = total;
+            if (total == 0) return;
+            velocity_shell_kernel<SO, T, ARITH><<<total, 256, 0, st>>>(ptrs(), Md.G, Md.sc, t0, t1, B);
+            check();
+        }
     }
 
     template <int SO, typename T, int ARITH> void staggered_step(int ti)
