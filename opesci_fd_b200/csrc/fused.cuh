@@ -107,7 +107,7 @@ template <int M> struct FusedCfg {
     static constexpr int VTILE = ((VZ * VY * 4 + 127) / 128) * 128;   // bytes, 128-B aligned for TMA
     static constexpr int STILE = EZ * EY * 4;
     static constexpr int SMEM = 3 * RD * VTILE + 5 * SR * STILE + 3 * RD * 8 + 128;
-    static constexpr int THREADS = EZ * EY;
+    static constexpr int THREADS = EZ / 2 * EY;             // two z-adjacent points per thread
 };
 
 struct FusedArgs {
@@ -118,6 +118,41 @@ struct FusedArgs {
     int xchunk;       // planes per x-chunk
 };
 
+// six consecutive floats p[-2..3] as three aligned 8-byte loads (p must be 8-byte aligned)
+__device__ __forceinline__ void load6(const float *p, float *f)
+{
+    const float2 a = *reinterpret_cast<const float2 *>(p - 2);
+    const float2 b = *reinterpret_cast<const float2 *>(p);
+    const float2 c = *reinterpret_cast<const float2 *>(p + 2);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y;
+}
+
+// global stores of results that nobody re-reads during this launch: streaming (evict-first) so
+// they do not push the halo rows that neighbouring CTAs still need out of L2
+#ifndef OPESCI_STREAM_STORES
+#define OPESCI_STREAM_STORES 1
+#endif
+__device__ __forceinline__ void gstore(float *p, float v)
+{
+#if OPESCI_STREAM_STORES
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void gstore2(float *p, float a, float b)
+{
+#if OPESCI_STREAM_STORES
+    __stcs(reinterpret_cast<float2 *>(p), make_float2(a, b));
+#else
+    *reinterpret_cast<float2 *>(p) = make_float2(a, b);
+#endif
+}
+
+// Each thread owns TWO z-adjacent points (lanes L = 0,1 at z0, z0+1): every shared/global access
+// along y and x is one 8-byte access for both points and the z-windows of both come from three
+// 8-byte loads, which halves the load/store-unit instruction count (the busiest pipe of the
+// one-point-per-thread version, ncu: profiles/r01_fused_v2_ncu_summary.txt).
 template <int SO, int ARITH>
 __global__ void __launch_bounds__(FusedCfg<SO / 2>::THREADS, 1)
 fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
@@ -138,8 +173,8 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 
     const GridGeom &G = A.G;
     const int tid = threadIdx.x;
-    const int tz = tid % K::EZ, ty = tid / K::EZ;
-    const int ye = blockIdx.y * K::CY + ty, ze = blockIdx.x * K::CZ + tz;   // global coords of this thread's point
+    const int tz = 2 * (tid % (K::EZ / 2)), ty = tid / (K::EZ / 2);          // lane 0 sits at tz, lane 1 at tz+1
+    const int ye = blockIdx.y * K::CY + ty, ze = blockIdx.x * K::CZ + tz;   // global coords of lane 0
     const int xa = M + blockIdx.z * A.xchunk;
     const int xb = min(xa + A.xchunk, G.dim[0] - M);
     const int xs_begin = max(M, xa - M), xs_end = min(G.dim[0] - M, xb + M);
@@ -173,10 +208,17 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
         }
     }
 
-    const bool inb = ye < G.dim[1] && ze < G.dim[2];
-    const bool core = ty >= M && ty < M + K::CY && tz >= M && tz < M + K::CZ;
-    const bool st_yz = core && ye >= M && ye < G.dim[1] - M && ze >= M && ze < G.dim[2] - M;
-    const bool vf_yz = core && ye >= 2 * M + 1 && ye < G.dim[1] - 2 * M - 1 && ze >= 2 * M + 1 && ze < G.dim[2] - 2 * M - 1;
+    // per-lane predicates
+    bool inb[2], st_yz[2], vf_yz[2];
+#pragma unroll
+    for (int L = 0; L < 2; ++L) {
+        const int z = ze + L, t = tz + L;
+        const bool core = ty >= M && ty < M + K::CY && t >= M && t < M + K::CZ;
+        inb[L] = ye < G.dim[1] && z < G.dim[2];
+        st_yz[L] = core && ye >= M && ye < G.dim[1] - M && z >= M && z < G.dim[2] - M;
+        vf_yz[L] = core && ye >= 2 * M + 1 && ye < G.dim[1] - 2 * M - 1 && z >= 2 * M + 1 && z < G.dim[2] - 2 * M - 1;
+    }
+    const bool inb2 = inb[0] && inb[1], st2 = st_yz[0] && st_yz[1], vf2 = vf_yz[0] && vf_yz[1];
     const int xv_lo = max(xa, 2 * M + 1), xv_hi = min(xb, G.dim[0] - 2 * M - 1);
     const long long pyz = (long long)ye * G.s[1] + ze;
     const long long lv0 = (long long)A.t0 * G.level, lv1 = (long long)A.t1 * G.level;
@@ -192,22 +234,35 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 #pragma unroll
     for (int k = 0; k < 3; ++k) gV1[k] = (T *)A.F.f[F_U + k] + lv1 + pyz;
 
-    // register state: own-column x-windows of the new stresses
-    T txx[2 * M], txy[2 * M + 1], txz[2 * M + 1];
+    // register state per lane: own-column x-windows of the new stresses
+    T txx[2][2 * M], txy[2][2 * M + 1], txz[2][2 * M + 1];
 #pragma unroll
-    for (int k = 0; k < 2 * M; ++k) txx[k] = 0;
+    for (int L = 0; L < 2; ++L) {
 #pragma unroll
-    for (int k = 0; k < 2 * M + 1; ++k) txy[k] = txz[k] = 0;
-    T vself = 0, wself = 0;                // V,W[t0] at plane xs-M (saved one iteration earlier)
-    const int lo = (ty + M) * K::VZ + tz + K::OFFZ;   // this thread's element inside a velocity tile
+        for (int k = 0; k < 2 * M; ++k) txx[L][k] = 0;
+#pragma unroll
+        for (int k = 0; k < 2 * M + 1; ++k) txy[L][k] = txz[L][k] = 0;
+    }
+    T vself[2] = {0, 0}, wself[2] = {0, 0};   // V,W[t0] at plane xs-M (saved one iteration earlier)
+    const int lo = (ty + M) * K::VZ + tz + K::OFFZ;   // lane 0's element inside a velocity tile (even => 8-B aligned)
     const T *vlo = vring + lo;
     T *slo = sring + ty * K::EZ + tz;
 
-    // T[t0] of the first plane
-    T told[6];
-    long long px = (long long)xs_begin * sx;
+    auto load_told = [&](T (*told)[6], long long px) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) told[k] = inb ? gT0[k][px] : (T)0;
+        for (int k = 0; k < 6; ++k) {
+            if (inb2) {
+                const float2 v = *reinterpret_cast<const float2 *>(gT0[k] + px);
+                told[0][k] = v.x; told[1][k] = v.y;
+            } else {
+                told[0][k] = inb[0] ? gT0[k][px] : (T)0;
+                told[1][k] = inb[1] ? gT0[k][px + 1] : (T)0;
+            }
+        }
+    };
+    T told[2][6];
+    long long px = (long long)xs_begin * sx;
+    load_told(told, px);
 
     // planes of the first window (first use of their slots: phase parity 0)
 #pragma unroll
@@ -224,8 +279,6 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             if (xs >= xs_end) break;
             // ---- the newest planes of this iteration: relative plane index RD*q + r + 2M-1
             {
-                constexpr int rel = 0;   // placeholder to keep the block scoped
-                (void)rel;
                 const int slot = (r + 2 * M - 1) % RD;
                 const uint32_t par = (uint32_t)(q + (r + 2 * M - 1) / RD) & 1u;
                 mbar_wait(&bars[0 * RD + slot], par);
@@ -233,94 +286,120 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                 mbar_wait(&bars[2 * RD + slot], par);
             }
             // ---- gather the operands of the six stress updates (all offsets are immediates)
-            T ux[2 * M], vx[2 * M], wx[2 * M];   // x-windows: U bwd (xs-M..xs+M-1), V,W fwd (xs-M+1..xs+M)
+            T ux[2][2 * M], vx[2][2 * M], wx[2][2 * M];   // x-windows: U bwd (xs-M..xs+M-1), V,W fwd (xs-M+1..xs+M)
 #pragma unroll
             for (int j = 0; j < 2 * M; ++j) {
                 const int slot = (r + j) % RD;
-                ux[j] = vlo[(0 * RD + slot) * VT];
-                vx[j] = vlo[(1 * RD + slot) * VT];
-                wx[j] = vlo[(2 * RD + slot) * VT];
+                const float2 a = *reinterpret_cast<const float2 *>(vlo + (0 * RD + slot) * VT);
+                const float2 b = *reinterpret_cast<const float2 *>(vlo + (1 * RD + slot) * VT);
+                const float2 c = *reinterpret_cast<const float2 *>(vlo + (2 * RD + slot) * VT);
+                ux[0][j] = a.x; ux[1][j] = a.y;
+                vx[0][j] = b.x; vx[1][j] = b.y;
+                wx[0][j] = c.x; wx[1][j] = c.y;
             }
             // plane xs: U is window entry M (slot r+M), V/W window entry M-1 (slot r+M-1)
             const T *pu = vlo + (0 * RD + (r + M) % RD) * VT;
             const T *pv = vlo + (1 * RD + (r + M - 1) % RD) * VT;
             const T *pw = vlo + (2 * RD + (r + M - 1) % RD) * VT;
-            T vy_b[2 * M], wz_b[2 * M];          // backward windows in-plane (normal stresses)
-            T uy_f[2 * M], uz_f[2 * M], vz_f[2 * M], wy_f[2 * M];   // forward windows in-plane (shear stresses)
+            T vy_b[2][2 * M], uy_f[2][2 * M], wy_f[2][2 * M];   // y-windows (bwd for the normal, fwd for the shear stresses)
 #pragma unroll
             for (int j = 0; j < 2 * M; ++j) {
-                vy_b[j] = pv[(j - M) * K::VZ];
-                wz_b[j] = pw[(j - M)];
-                uy_f[j] = pu[(j - M + 1) * K::VZ];
-                uz_f[j] = pu[(j - M + 1)];
-                vz_f[j] = pv[(j - M + 1)];
-                wy_f[j] = pw[(j - M + 1) * K::VZ];
+                const float2 a = *reinterpret_cast<const float2 *>(pv + (j - M) * K::VZ);
+                const float2 b = *reinterpret_cast<const float2 *>(pu + (j - M + 1) * K::VZ);
+                const float2 c = *reinterpret_cast<const float2 *>(pw + (j - M + 1) * K::VZ);
+                vy_b[0][j] = a.x; vy_b[1][j] = a.y;
+                uy_f[0][j] = b.x; uy_f[1][j] = b.y;
+                wy_f[0][j] = c.x; wy_f[1][j] = c.y;
             }
-            const T uself = ux[0];               // U[t0] at plane xs-M (velocity self term of this iteration)
-            const T vself_next = vx[0], wself_next = wx[0];   // V,W[t0] at plane xs-M+1
-            T tn[6];
-            if (ARITH == OPESCI_ARITH_REFERENCE) {
+            T fu[6], fv[6], fw[6];                // z rows z0-2 .. z0+3 of plane xs
+            load6(pu, fu);
+            load6(pv, fv);
+            load6(pw, fw);
+            T tn[2][6], uself[2], vself_next[2], wself_next[2];
 #pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    T acc = told[a];
-                    bool first = false;
-                    window_ref_arr<M, T, false>(acc, first, ux, A.C.sn[a][0]);
-                    window_ref_arr<M, T, false>(acc, first, vy_b, A.C.sn[a][1]);
-                    window_ref_arr<M, T, false>(acc, first, wz_b, A.C.sn[a][2]);
-                    tn[a] = acc;
-                }
-                {
-                    T acc = told[3]; bool first = false;   // Txy: D_y U, D_x V
-                    window_ref_arr<M, T, true>(acc, first, uy_f, A.C.ss[0][0]);
-                    window_ref_arr<M, T, true>(acc, first, vx, A.C.ss[0][1]);
-                    tn[3] = acc;
-                }
-                {
-                    T acc = told[4]; bool first = false;   // Tyz: D_z V, D_y W
-                    window_ref_arr<M, T, true>(acc, first, vz_f, A.C.ss[1][0]);
-                    window_ref_arr<M, T, true>(acc, first, wy_f, A.C.ss[1][1]);
-                    tn[4] = acc;
-                }
-                {
-                    T acc = told[5]; bool first = false;   // Txz: D_z U, D_x W
-                    window_ref_arr<M, T, true>(acc, first, uz_f, A.C.ss[2][0]);
-                    window_ref_arr<M, T, true>(acc, first, wx, A.C.ss[2][1]);
-                    tn[5] = acc;
-                }
-            } else {
+            for (int L = 0; L < 2; ++L) {
+                T wz_b[2 * M], uz_f[2 * M], vz_f[2 * M];
 #pragma unroll
-                for (int a = 0; a < 3; ++a)
-                    tn[a] = told[a] + (window_fast_arr<M, T, false>(ux, A.C.sn[a][0]) + window_fast_arr<M, T, false>(vy_b, A.C.sn[a][1]) +
-                                       window_fast_arr<M, T, false>(wz_b, A.C.sn[a][2]));
-                tn[3] = told[3] + (window_fast_arr<M, T, true>(uy_f, A.C.ss[0][0]) + window_fast_arr<M, T, true>(vx, A.C.ss[0][1]));
-                tn[4] = told[4] + (window_fast_arr<M, T, true>(vz_f, A.C.ss[1][0]) + window_fast_arr<M, T, true>(wy_f, A.C.ss[1][1]));
-                tn[5] = told[5] + (window_fast_arr<M, T, true>(uz_f, A.C.ss[2][0]) + window_fast_arr<M, T, true>(wx, A.C.ss[2][1]));
+                for (int j = 0; j < 2 * M; ++j) {
+                    wz_b[j] = fw[2 + L - M + j];
+                    uz_f[j] = fu[2 + L - M + 1 + j];
+                    vz_f[j] = fv[2 + L - M + 1 + j];
+                }
+                uself[L] = ux[L][0];               // U[t0] at plane xs-M (velocity self term of this iteration)
+                vself_next[L] = vx[L][0];          // V,W[t0] at plane xs-M+1
+                wself_next[L] = wx[L][0];
+                if (ARITH == OPESCI_ARITH_REFERENCE) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        T acc = told[L][a];
+                        bool first = false;
+                        window_ref_arr<M, T, false>(acc, first, ux[L], A.C.sn[a][0]);
+                        window_ref_arr<M, T, false>(acc, first, vy_b[L], A.C.sn[a][1]);
+                        window_ref_arr<M, T, false>(acc, first, wz_b, A.C.sn[a][2]);
+                        tn[L][a] = acc;
+                    }
+                    {
+                        T acc = told[L][3]; bool first = false;   // Txy: D_y U, D_x V
+                        window_ref_arr<M, T, true>(acc, first, uy_f[L], A.C.ss[0][0]);
+                        window_ref_arr<M, T, true>(acc, first, vx[L], A.C.ss[0][1]);
+                        tn[L][3] = acc;
+                    }
+                    {
+                        T acc = told[L][4]; bool first = false;   // Tyz: D_z V, D_y W
+                        window_ref_arr<M, T, true>(acc, first, vz_f, A.C.ss[1][0]);
+                        window_ref_arr<M, T, true>(acc, first, wy_f[L], A.C.ss[1][1]);
+                        tn[L][4] = acc;
+                    }
+                    {
+                        T acc = told[L][5]; bool first = false;   // Txz: D_z U, D_x W
+                        window_ref_arr<M, T, true>(acc, first, uz_f, A.C.ss[2][0]);
+                        window_ref_arr<M, T, true>(acc, first, wx[L], A.C.ss[2][1]);
+                        tn[L][5] = acc;
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+                        tn[L][a] = told[L][a] + (window_fast_arr<M, T, false>(ux[L], A.C.sn[a][0]) +
+                                                 window_fast_arr<M, T, false>(vy_b[L], A.C.sn[a][1]) +
+                                                 window_fast_arr<M, T, false>(wz_b, A.C.sn[a][2]));
+                    tn[L][3] = told[L][3] + (window_fast_arr<M, T, true>(uy_f[L], A.C.ss[0][0]) + window_fast_arr<M, T, true>(vx[L], A.C.ss[0][1]));
+                    tn[L][4] = told[L][4] + (window_fast_arr<M, T, true>(vz_f, A.C.ss[1][0]) + window_fast_arr<M, T, true>(wy_f[L], A.C.ss[1][1]));
+                    tn[L][5] = told[L][5] + (window_fast_arr<M, T, true>(uz_f, A.C.ss[2][0]) + window_fast_arr<M, T, true>(wx[L], A.C.ss[2][1]));
+                }
             }
             // ---- store the new stresses (owned tile, owned planes), prefetch next T[t0]
-            if (st_yz && xs >= xa && xs < xb) {
+            if (xs >= xa && xs < xb) {
+                if (st2) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) gT1[k][px] = tn[k];
+                    for (int k = 0; k < 6; ++k) gstore2(gT1[k] + px, tn[0][k], tn[1][k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        if (st_yz[0]) gstore(gT1[k] + px, tn[0][k]);
+                        if (st_yz[1]) gstore(gT1[k] + px + 1, tn[1][k]);
+                    }
+                }
             }
             px += sx;
-            if (xs + 1 < xs_end) {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) told[k] = inb ? gT0[k][px] : (T)0;
-            }
+            if (xs + 1 < xs_end) load_told(told, px);
             // ---- shift the register windows, publish the in-plane operands
 #pragma unroll
-            for (int k = 0; k < 2 * M - 1; ++k) txx[k] = txx[k + 1];
-            txx[2 * M - 1] = tn[0];
+            for (int L = 0; L < 2; ++L) {
 #pragma unroll
-            for (int k = 0; k < 2 * M; ++k) { txy[k] = txy[k + 1]; txz[k] = txz[k + 1]; }
-            txy[2 * M] = tn[3];
-            txz[2 * M] = tn[5];
+                for (int k = 0; k < 2 * M - 1; ++k) txx[L][k] = txx[L][k + 1];
+                txx[L][2 * M - 1] = tn[L][0];
+#pragma unroll
+                for (int k = 0; k < 2 * M; ++k) { txy[L][k] = txy[L][k + 1]; txz[L][k] = txz[L][k + 1]; }
+                txy[L][2 * M] = tn[L][3];
+                txz[L][2 * M] = tn[L][5];
+            }
             {
                 T *s = slo + (xs & (K::SR - 1)) * ST;
-                s[0 * K::SR * ST] = tn[3];   // Txy
-                s[1 * K::SR * ST] = tn[5];   // Txz
-                s[2 * K::SR * ST] = tn[1];   // Tyy
-                s[3 * K::SR * ST] = tn[4];   // Tyz
-                s[4 * K::SR * ST] = tn[2];   // Tzz
+                *reinterpret_cast<float2 *>(s + 0 * K::SR * ST) = make_float2(tn[0][3], tn[1][3]);   // Txy
+                *reinterpret_cast<float2 *>(s + 1 * K::SR * ST) = make_float2(tn[0][5], tn[1][5]);   // Txz
+                *reinterpret_cast<float2 *>(s + 2 * K::SR * ST) = make_float2(tn[0][1], tn[1][1]);   // Tyy
+                *reinterpret_cast<float2 *>(s + 3 * K::SR * ST) = make_float2(tn[0][4], tn[1][4]);   // Tyz
+                *reinterpret_cast<float2 *>(s + 4 * K::SR * ST) = make_float2(tn[0][2], tn[1][2]);   // Tzz
             }
             __syncthreads();
             // ---- the oldest planes (window entry 0, slot r) are dead: refill their slots
@@ -339,54 +418,75 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             }
             // ---- velocities of plane xv = xs - M from the new stresses xv-M .. xv+M
             const int xv = xs - M;
-            if (vf_yz && xv >= xv_lo && xv < xv_hi) {
+            if ((vf_yz[0] || vf_yz[1]) && xv >= xv_lo && xv < xv_hi) {
                 const T *s = slo + (xv & (K::SR - 1)) * ST;
                 const T *sxy = s, *sxz = s + 1 * K::SR * ST, *syy = s + 2 * K::SR * ST, *syz = s + 3 * K::SR * ST,
                         *szz = s + 4 * K::SR * ST;
-                T xy_yb[2 * M], xz_zb[2 * M], yy_yf[2 * M], yz_zb[2 * M], yz_yb[2 * M], zz_zf[2 * M];
+                T xy_yb[2][2 * M], yy_yf[2][2 * M], yz_yb[2][2 * M];
 #pragma unroll
                 for (int j = 0; j < 2 * M; ++j) {
-                    xy_yb[j] = sxy[(j - M) * K::EZ];
-                    xz_zb[j] = sxz[(j - M)];
-                    yy_yf[j] = syy[(j - M + 1) * K::EZ];
-                    yz_zb[j] = syz[(j - M)];
-                    yz_yb[j] = syz[(j - M) * K::EZ];
-                    zz_zf[j] = szz[(j - M + 1)];
+                    const float2 a = *reinterpret_cast<const float2 *>(sxy + (j - M) * K::EZ);
+                    const float2 b = *reinterpret_cast<const float2 *>(syy + (j - M + 1) * K::EZ);
+                    const float2 c = *reinterpret_cast<const float2 *>(syz + (j - M) * K::EZ);
+                    xy_yb[0][j] = a.x; xy_yb[1][j] = a.y;
+                    yy_yf[0][j] = b.x; yy_yf[1][j] = b.y;
+                    yz_yb[0][j] = c.x; yz_yb[1][j] = c.y;
                 }
-                // x-windows from registers: Txx fwd = planes xv-M+1..xv+M = txx[0..2M-1];
-                // Txy, Txz bwd = planes xv-M..xv+M-1 = txy[0..2M-1]
-                T un, vn, wn;
-                if (ARITH == OPESCI_ARITH_REFERENCE) {
-                    T acc = 0; bool first = true;
-                    window_ref_arr<M, T, true>(acc, first, txx, A.C.v[0][0]);
-                    window_ref_arr<M, T, false>(acc, first, xy_yb, A.C.v[0][1]);
-                    window_ref_arr<M, T, false>(acc, first, xz_zb, A.C.v[0][2]);
-                    un = add_rn<T>(acc, uself);
-                    acc = 0; first = true;
-                    window_ref_arr<M, T, false>(acc, first, txy, A.C.v[1][0]);
-                    window_ref_arr<M, T, true>(acc, first, yy_yf, A.C.v[1][1]);
-                    window_ref_arr<M, T, false>(acc, first, yz_zb, A.C.v[1][2]);
-                    vn = add_rn<T>(acc, vself);
-                    acc = 0; first = true;
-                    window_ref_arr<M, T, false>(acc, first, txz, A.C.v[2][0]);
-                    window_ref_arr<M, T, false>(acc, first, yz_yb, A.C.v[2][1]);
-                    window_ref_arr<M, T, true>(acc, first, zz_zf, A.C.v[2][2]);
-                    wn = add_rn<T>(acc, wself);
-                } else {
-                    un = uself + (window_fast_arr<M, T, true>(txx, A.C.v[0][0]) + window_fast_arr<M, T, false>(xy_yb, A.C.v[0][1]) +
-                                  window_fast_arr<M, T, false>(xz_zb, A.C.v[0][2]));
-                    vn = vself + (window_fast_arr<M, T, false>(txy, A.C.v[1][0]) + window_fast_arr<M, T, true>(yy_yf, A.C.v[1][1]) +
-                                  window_fast_arr<M, T, false>(yz_zb, A.C.v[1][2]));
-                    wn = wself + (window_fast_arr<M, T, false>(txz, A.C.v[2][0]) + window_fast_arr<M, T, false>(yz_yb, A.C.v[2][1]) +
-                                  window_fast_arr<M, T, true>(zz_zf, A.C.v[2][2]));
+                T fxz[6], fyz[6], fzz[6];
+                load6(sxz, fxz);
+                load6(syz, fyz);
+                load6(szz, fzz);
+                T vout[2][3];
+#pragma unroll
+                for (int L = 0; L < 2; ++L) {
+                    T xz_zb[2 * M], yz_zb[2 * M], zz_zf[2 * M];
+#pragma unroll
+                    for (int j = 0; j < 2 * M; ++j) {
+                        xz_zb[j] = fxz[2 + L - M + j];
+                        yz_zb[j] = fyz[2 + L - M + j];
+                        zz_zf[j] = fzz[2 + L - M + 1 + j];
+                    }
+                    // x-windows from registers: Txx fwd = planes xv-M+1..xv+M = txx[0..2M-1];
+                    // Txy, Txz bwd = planes xv-M..xv+M-1 = txy[0..2M-1]
+                    if (ARITH == OPESCI_ARITH_REFERENCE) {
+                        T acc = 0; bool first = true;
+                        window_ref_arr<M, T, true>(acc, first, txx[L], A.C.v[0][0]);
+                        window_ref_arr<M, T, false>(acc, first, xy_yb[L], A.C.v[0][1]);
+                        window_ref_arr<M, T, false>(acc, first, xz_zb, A.C.v[0][2]);
+                        vout[L][0] = add_rn<T>(acc, uself[L]);
+                        acc = 0; first = true;
+                        window_ref_arr<M, T, false>(acc, first, txy[L], A.C.v[1][0]);
+                        window_ref_arr<M, T, true>(acc, first, yy_yf[L], A.C.v[1][1]);
+                        window_ref_arr<M, T, false>(acc, first, yz_zb, A.C.v[1][2]);
+                        vout[L][1] = add_rn<T>(acc, vself[L]);
+                        acc = 0; first = true;
+                        window_ref_arr<M, T, false>(acc, first, txz[L], A.C.v[2][0]);
+                        window_ref_arr<M, T, false>(acc, first, yz_yb[L], A.C.v[2][1]);
+                        window_ref_arr<M, T, true>(acc, first, zz_zf, A.C.v[2][2]);
+                        vout[L][2] = add_rn<T>(acc, wself[L]);
+                    } else {
+                        vout[L][0] = uself[L] + (window_fast_arr<M, T, true>(txx[L], A.C.v[0][0]) + window_fast_arr<M, T, false>(xy_yb[L], A.C.v[0][1]) +
+                                                 window_fast_arr<M, T, false>(xz_zb, A.C.v[0][2]));
+                        vout[L][1] = vself[L] + (window_fast_arr<M, T, false>(txy[L], A.C.v[1][0]) + window_fast_arr<M, T, true>(yy_yf[L], A.C.v[1][1]) +
+                                                 window_fast_arr<M, T, false>(yz_zb, A.C.v[1][2]));
+                        vout[L][2] = wself[L] + (window_fast_arr<M, T, false>(txz[L], A.C.v[2][0]) + window_fast_arr<M, T, false>(yz_yb[L], A.C.v[2][1]) +
+                                                 window_fast_arr<M, T, true>(zz_zf, A.C.v[2][2]));
+                    }
                 }
                 const long long pxv = px - (long long)(M + 1) * sx;   // px already points at plane xs+1
-                gV1[0][pxv] = un;
-                gV1[1][pxv] = vn;
-                gV1[2][pxv] = wn;
+                if (vf2) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) gstore2(gV1[k] + pxv, vout[0][k], vout[1][k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        if (vf_yz[0]) gstore(gV1[k] + pxv, vout[0][k]);
+                        if (vf_yz[1]) gstore(gV1[k] + pxv + 1, vout[1][k]);
+                    }
+                }
             }
-            vself = vself_next;
-            wself = wself_next;
+#pragma unroll
+            for (int L = 0; L < 2; ++L) { vself[L] = vself_next[L]; wself[L] = wself_next[L]; }
         }
     }
 }
