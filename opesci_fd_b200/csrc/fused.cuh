@@ -132,6 +132,17 @@ __device__ __forceinline__ void load6(const float *p, float *f)
 #ifndef OPESCI_STREAM_STORES
 #define OPESCI_STREAM_STORES 1
 #endif
+#ifndef OPESCI_T0_NOALLOC
+#define OPESCI_T0_NOALLOC 0
+#endif
+// T[t0] is read exactly once per launch (plus the recomputed halo): do not allocate it in L1, whose
+// capacity is what is left of the 228 KB after the shared-memory rings
+__device__ __forceinline__ float2 gload2_stream(const float *p)
+{
+    float2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void gstore(float *p, float v)
 {
 #if OPESCI_STREAM_STORES
@@ -252,7 +263,11 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             if (inb2) {
+#if OPESCI_T0_NOALLOC
+                const float2 v = gload2_stream(gT0[k] + px);
+#else
                 const float2 v = *reinterpret_cast<const float2 *>(gT0[k] + px);
+#endif
                 told[0][k] = v.x; told[1][k] = v.y;
             } else {
                 told[0][k] = inb[0] ? gT0[k][px] : (T)0;
