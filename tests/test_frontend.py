@@ -1,0 +1,152 @@
+"""CPU: the host front end (reference API mirror) and the C ABI.
+
+ * FD weights against the table the reference's sympy derivation produces;
+ * every float literal of the lowered model against the literals printed in the reference's
+   generated sources (tests/golden/literals.json), term by term and in emitted order;
+ * the typed C-expression evaluator against C semantics;
+ * the CUDA library loads and exports every symbol include/opesci_b200.h declares (no compute).
+"""
+import ctypes
+import json
+import os
+import re
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from common import GOLDEN, ROOT, load_golden, load_norms, make_grid
+from opesci_fd_b200 import abi, cexpr
+from opesci_fd_b200.codeprinter import literal, literal_text
+from opesci_fd_b200.util import central_weights, staggered_first_weights
+
+LITERALS = json.load(open(os.path.join(GOLDEN, "literals.json")))
+
+
+def test_staggered_fd_weights_match_reference_table():
+    # SURVEY.md 8a, derived by the reference's Taylor-matrix inversion (opesci/util.py:103-118,195-236)
+    table = {2: ["1"], 4: ["9/8", "-1/24"], 6: ["75/64", "-25/384", "3/640"],
+             8: ["1225/1024", "-245/3072", "49/5120", "-5/7168"],
+             10: ["19845/16384", "-735/8192", "567/40960", "-405/229376", "35/294912"],
+             12: ["160083/131072", "-12705/131072", "22869/1310720", "-5445/1835008", "847/2359296", "-63/2883584"]}
+    for so, coefs in table.items():
+        assert staggered_first_weights(so // 2) == [Fraction(c) for c in coefs]
+    assert central_weights(2, 2) == [Fraction(-5, 2), Fraction(4, 3), Fraction(-1, 12)]
+
+
+def test_literal_rounding_rule():
+    # 15 significant digits, then a float literal (opesci/codeprinter.py:46-63)
+    assert literal_text(9.0 / 8 * 0.2 / 27) == "8.33333333333333e-3"
+    assert literal_text(0.225) == "2.25e-1"
+    assert literal(1.0 / 3) == np.float32(float("3.33333333333333e-1"))
+
+
+def _emitted_order_staggered(p, m):
+    """Signed literals of the nine interior sums in the order the printer emits them."""
+    def window(c, fwd):
+        c = [float(np.float32(x)) for x in c[:m]]
+        if fwd:
+            return c + [-x for x in c[1:]] + [-c[0]]
+        return c[1:] + [-x for x in c] + [c[0]]
+    out = {}
+    for a, name in enumerate(["Txx", "Tyy", "Tzz"]):
+        out[name] = sum((window(p.c_stress_normal[a][d], False) for d in range(3)), [])
+    for s, name in enumerate(["Txy", "Tyz", "Txz"]):
+        out[name] = window(p.c_stress_shear[s][0], True) + window(p.c_stress_shear[s][1], True)
+    for a, name in enumerate(["U", "V", "W"]):
+        out[name] = sum((window(p.c_velocity[a][d], d == a) for d in range(3)), [])
+    return out
+
+
+def _config(name):
+    if os.path.exists(os.path.join(GOLDEN, name + ".npz")):
+        return load_golden(name)[0]
+    return load_norms()[name]["config"]
+
+
+@pytest.mark.parametrize("name", sorted(n for n in LITERALS if n.startswith("ew_")))
+def test_lowered_staggered_literals_equal_generated_source(name):
+    cfg = _config(name)
+    grid = make_grid(cfg)
+    p, keep = grid.build_params()
+    mine = _emitted_order_staggered(p, cfg["so"] // 2)
+    for field, lits in LITERALS[name].items():
+        ref = [float(np.float32(float(x))) for x in lits]
+        assert mine[field] == ref, "%s: literals of %s differ from the generated source" % (name, field)
+
+
+@pytest.mark.parametrize("name", sorted(n for n in LITERALS if n.startswith("sw_")))
+def test_lowered_acoustic_literals_equal_generated_source(name):
+    cfg = _config(name)
+    grid = make_grid(cfg)
+    p, keep = grid.build_params()
+    m = cfg["so"] // 2
+    mine = []
+    for d in range(3):
+        c = [float(np.float32(p.ac_coef[d][k])) for k in range(m)]
+        if any(c):
+            mine += c + c
+    mine.append(float(np.float32(p.ac_centre)))
+    ref = [float(np.float32(float(x))) for x in LITERALS[name]["MAIN_GRID"]]
+    assert mine == ref
+
+
+def test_cexpr_types_like_cxx():
+    import math
+    v = cexpr.Variables()
+    v.scalar("beta", cexpr.FLOAT, 0.7692307692307692)
+    v.scalar("mu", cexpr.FLOAT, 1.0530000000000002)
+    v.axis("x", cexpr.FLOAT, 0, np.float32(0.1) * np.arange(5, dtype=np.float32))
+    v.axis("y", cexpr.FLOAT, 1, np.float32(0.2) * np.arange(4, dtype=np.float32))
+    prog = cexpr.compile_expression("(sin(M_PI*y) - 2.0e-3F*x)*cos(1.0e-3F*M_SQRT2*M_PI*sqrt(beta*mu))", v, [5, 4, 3])
+    bm = np.float32(0.7692307692307692) * np.float32(1.0530000000000002)            # float*float stays float
+    c = math.cos(float(np.float32(1.0e-3)) * 1.41421356237309504880 * 3.14159265358979323846 * math.sqrt(float(bm)))
+    for ix in range(5):
+        for iy in range(4):
+            xs = np.float32(0.1) * np.float32(ix)
+            ys = np.float32(0.2) * np.float32(iy)
+            want = (math.sin(3.14159265358979323846 * float(ys)) - float(np.float32(2.0e-3) * xs)) * c
+            assert prog.evaluate(ix, iy, 0) == want
+
+
+def test_unsupported_models_raise():
+    import eigenwave3d as drv
+    with pytest.raises(NotImplementedError):
+        drv.eigenwave3d((1.0, 1.0, 1.0), (10, 10, 10), 0.002, 0.01, accuracy_order=[2, 4, 4, 4], read=True, verbose=False)
+    g = drv.eigenwave3d((1.0, 1.0, 1.0), (10, 10, 10), 0.002, 0.01, accuracy_order=[2, 4, 4, 4], verbose=False)
+    g._free_surface.discard((3, 1))
+    with pytest.raises(NotImplementedError):
+        g.build_params()
+
+
+def test_cuda_library_exports_the_abi(cuda_lib):
+    # loading + symbol lookup only: no compute without a GPU
+    hdr = open(os.path.join(ROOT, "include", "opesci_b200.h")).read()
+    declared = set(re.findall(r"\b(opesci_\w+)\s*\(", hdr))
+    assert declared >= {"opesci_execute", "opesci_convergence", "opesci_free", "opesci_b200_configure"}
+    for sym in declared:
+        assert hasattr(cuda_lib, sym), "libopesci_b200.so does not export %s" % sym
+    assert cuda_lib.opesci_b200_is_cuda() == 1
+    bad = abi.OpesciB200Params()
+    assert cuda_lib.opesci_b200_configure(ctypes.byref(bad)) != 0        # struct_size check, no GPU needed
+
+
+def test_product_path_never_touches_the_oracle():
+    # the package must not import / load anything under oracle/ (oracle = test infrastructure)
+    pkg = os.path.join(ROOT, "opesci_fd_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "libopesci_oracle" not in text, f
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_generate_writes_model_description(tmp_path):
+    import eigenwave3d as drv
+    g = drv.eigenwave3d((1.0, 1.0, 1.0), (12, 12, 12), 0.002, 0.01, accuracy_order=[2, 4, 4, 4], verbose=False)
+    out = tmp_path / "model.json"
+    g.generate(str(out))
+    desc = json.loads(out.read_text())
+    assert desc["dim"] == [17, 17, 17] and desc["so"] == 4 and desc["free_surface"] == abi.FS_LEVANDER
+    assert abs(desc["c_stress_normal"][0][0][0] - 9.0 / 8 * 0.002 * 12 * 1.0) < 1e-6
