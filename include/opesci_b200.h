@@ -126,7 +126,8 @@ typedef struct OpesciB200Params {
     int32_t free_surface;        /* 1: Levander (so==4), 2: Robertsson (so!=4), 0: none (staggeredgrid.py:223-226) */
     int32_t flags;
     int32_t warmup_steps;        /* the first `warmup_steps` of `ntsteps` are excluded from the loop timing */
-    int32_t reserved_i[2];
+    int32_t slab_rank;           /* x-slab decomposition: this process's rank ... */
+    int32_t slab_nranks;         /* ... of slab_nranks (0 or 1: single domain).  dim[0] is always the GLOBAL dim1 */
     double dt;
     double dx[3];
     double volume_literal;       /* dx1*dx2*dx3 as printed (float literal) for the L2 scale */
@@ -179,6 +180,16 @@ int opesci_b200_last_timing(double *loop_seconds, double *points_per_step, int64
  * out_ms[0] = stress (or fused stress+velocity) kernel, out_ms[1] = velocity kernel (0 if fused),
  * out_ms[2] = all ghost-cell loops of one step.  Advances the fields; call it last. */
 int opesci_b200_time_kernels(OpesciGrid *grid, int reps, double *out_ms);
+/* ---- multi-GPU: x-slab decomposition (no reference counterpart: the reference is OpenMP only) ----
+ * One process per GPU.  dim1 is split into contiguous slabs; every rank keeps OPESCI_SLAB_HALO planes
+ * of all fields on each inner side, computes a whole time step on its local slab (x-face loops only
+ * on the first / last rank) and then refreshes the halo planes by NCCL send/recv.  The host
+ * distributes the 128-byte NCCL unique id (rank 0 creates it), e.g. with torch.distributed. */
+#define OPESCI_SLAB_HALO 8       /* >= 2m+3 for so=4: stress m, velocity m, Levander ghost chain 3 per step */
+#define OPESCI_COMM_ID_BYTES 128
+int opesci_b200_comm_unique_id(void *out_id, int nbytes);
+int opesci_b200_comm_init(int rank, int nranks, const void *id, int nbytes);
+int opesci_b200_comm_finalize(void);
 /* 1 if this library was built with the CUDA kernels (0 for the CPU oracle build) */
 int opesci_b200_is_cuda(void);
 

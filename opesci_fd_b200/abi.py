@@ -64,7 +64,7 @@ class OpesciB200Params(Structure):
         ("struct_size", c_uint32), ("kind", c_int32), ("so", c_int32), ("is_double", c_int32),
         ("dim", c_int32 * 3), ("ntsteps", c_int32), ("nfields", c_int32), ("nlevels", c_int32),
         ("converge", c_int32), ("free_surface", c_int32), ("flags", c_int32),
-        ("warmup_steps", c_int32), ("reserved_i", c_int32 * 2),
+        ("warmup_steps", c_int32), ("slab_rank", c_int32), ("slab_nranks", c_int32),
         ("dt", c_double), ("dx", c_double * 3), ("volume_literal", c_double),
         ("c_stress_normal", ((c_float * OPESCI_MAX_M) * 3) * 3),
         ("c_stress_shear", ((c_float * OPESCI_MAX_M) * 2) * 3),
@@ -85,7 +85,10 @@ EXPORTED_SYMBOLS = [
     "opesci_b200_configure", "opesci_execute", "opesci_convergence", "opesci_free",
     "opesci_b200_last_error", "opesci_b200_convergence_f64", "opesci_b200_last_timing",
     "opesci_b200_is_cuda", "opesci_b200_time_kernels",
+    "opesci_b200_comm_unique_id", "opesci_b200_comm_init", "opesci_b200_comm_finalize",
 ]
+SLAB_HALO = 8
+COMM_ID_BYTES = 128
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CUDA_LIBRARY = os.path.join(_PKG_DIR, "csrc", "libopesci_b200.so")
@@ -110,6 +113,13 @@ def bind(lib):
     if hasattr(lib, "opesci_b200_time_kernels"):
         lib.opesci_b200_time_kernels.argtypes = [POINTER(OpesciGrid), ctypes.c_int, POINTER(c_double)]
         lib.opesci_b200_time_kernels.restype = ctypes.c_int
+    if hasattr(lib, "opesci_b200_comm_init"):
+        lib.opesci_b200_comm_unique_id.argtypes = [c_void_p, ctypes.c_int]
+        lib.opesci_b200_comm_unique_id.restype = ctypes.c_int
+        lib.opesci_b200_comm_init.argtypes = [ctypes.c_int, ctypes.c_int, c_void_p, ctypes.c_int]
+        lib.opesci_b200_comm_init.restype = ctypes.c_int
+        lib.opesci_b200_comm_finalize.argtypes = []
+        lib.opesci_b200_comm_finalize.restype = ctypes.c_int
     lib.opesci_b200_is_cuda.argtypes = []
     lib.opesci_b200_is_cuda.restype = ctypes.c_int
     return lib

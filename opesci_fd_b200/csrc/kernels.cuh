@@ -304,7 +304,7 @@ __global__ void face_mirror(T *__restrict__ A /* level base */, GridGeom G, Mirr
 struct FaceLoop {
     int kind;           // 0: plane assignments (MirrorOps)   1: emitted sum (DevEq)
     int d, n;           // face normal axis; target plane (equation loops)
-    int lo, hi1, hi2;   // ranges [lo,hi1) x [lo,hi2) on the other two axes (e1 < e2)
+    int lo1, lo, hi1, hi2;   // ranges [lo1,hi1) x [lo,hi2) on the other two axes (e1 < e2)
     int field, level;   // mirror loops: array and time level
     int lv0, lv1;       // equation loops: time levels of slots 0 / 1
     MirrorOps ops;
@@ -333,7 +333,7 @@ face_batch(FieldPtrs F, GridGeom G, const __grid_constant__ FaceBatch B)
     // threads run along e2 (contiguous z) except on z-faces, where 8 x 32 tiles keep a little locality
     const int w = (d == 2) ? 8 : 128, h = 256 / w;
     const int j = L.lo + bx * w + (int)(threadIdx.x % w);
-    const int i = L.lo + by * h + (int)(threadIdx.x / w);
+    const int i = L.lo1 + by * h + (int)(threadIdx.x / w);
     if (i >= L.hi1 || j >= L.hi2) return;
     const long long q = (long long)i * G.s[e1] + (long long)j * G.s[e2];
     if (L.kind == 0) {

@@ -20,6 +20,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
+#include "../../include/opesci_slab.h"
 #include "fused.cuh"
 #include "kernels.cuh"
 
@@ -39,7 +42,62 @@ int fail(const char *fmt, const char *a = "", const char *b = "")
         if (e_ != cudaSuccess) return fail("CUDA error: %s at %s", cudaGetErrorString(e_), #call); \
     } while (0)
 
-struct Launch;   // one recorded kernel launch of a time step
+
+// ------------------------------------------------------------------ NCCL (bound at run time)
+// Only needed for slab_nranks > 1; the library itself does not link against NCCL, it uses the copy
+// already loaded into the process (torch's bundled libnccl.so.2) or dlopens one.
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat64 = 8, ncclUint8 = 1 };
+enum { ncclSum = 0 };
+struct Nccl {
+    void *handle = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+} g_nccl;
+
+int nccl_bind()
+{
+    if (g_nccl.GetUniqueId) return 0;
+    void *h = dlopen(nullptr, RTLD_NOW);                       // already in the process (torch)?
+    if (!h || !dlsym(h, "ncclCommInitRank")) {
+        const char *names[] = {"libnccl.so.2", "libnccl.so",
+                               "/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/lib/libnccl.so.2"};
+        h = nullptr;
+        for (const char *n : names)
+            if ((h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    }
+    if (!h) return fail("NCCL not found (dlopen libnccl.so.2 failed): %s", dlerror());
+    g_nccl.handle = h;
+#define BIND(field, sym) *(void **)(&g_nccl.field) = dlsym(h, sym); if (!g_nccl.field) return fail("NCCL symbol missing: %s", sym)
+    BIND(GetUniqueId, "ncclGetUniqueId");
+    BIND(CommInitRank, "ncclCommInitRank");
+    BIND(CommDestroy, "ncclCommDestroy");
+    BIND(Send, "ncclSend");
+    BIND(Recv, "ncclRecv");
+    BIND(GroupStart, "ncclGroupStart");
+    BIND(GroupEnd, "ncclGroupEnd");
+    BIND(AllReduce, "ncclAllReduce");
+    BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+    return 0;
+}
+#define NCCL_OK(call)                                                                           \
+    do {                                                                                        \
+        int r_ = (call);                                                                        \
+        if (r_ != ncclSuccess) return fail("NCCL error: %s at %s", g_nccl.GetErrorString(r_), #call); \
+    } while (0)
+
 
 struct Model {
     OpesciB200Params p;
@@ -52,6 +110,7 @@ struct Model {
     DevEq lev_vel_eq[3][3][2];
     std::vector<double> tables;                  // host copy of every table
     std::vector<size_t> table_off[OPESCI_MAX_FIELDS][2];
+    OpesciSlab slab;                              // x-slab of this rank (whole domain when nranks == 1)
 };
 Model g_model;
 
@@ -247,38 +306,56 @@ struct Stepper {
             const int w = L.d == 2 ? 8 : 128, h = 256 / w;
             B.nbx[k] = (L.hi2 - L.lo + w - 1) / w;
             B.start[k] = total;
-            total += B.nbx[k] * ((L.hi1 - L.lo + h - 1) / h);
+            total += B.nbx[k] * ((L.hi1 - L.lo1 + h - 1) / h);
         }
         B.start[B.count] = total;
         face_batch<T><<<total, 256, 0, st>>>(ptrs(), M.G, B);
         check();
     }
-    bool add_mirror(FaceBatch &B, int field, int level, int d, const MirrorOps &ops, int lo, int himargin) const
+    // loop ranges of one ghost loop: the reference uses [lo, dim - himargin) on both free axes
+    // (staggeredgrid.py:785-796, 844-845).  On an artificial slab end the x range of the Levander
+    // stress loops (lo = m+1) is widened by one plane: plane m / ldim-m-1 is an ordinary interior
+    // plane there, and everything stays >= m planes away from the end of the local array.
+    void set_ranges(FaceLoop &L, int d, int lo, int himargin) const
     {
         const Model &M = R.M;
         const int e1 = d == 0 ? 1 : 0, e2 = d == 2 ? 1 : 2;
+        L.lo1 = lo; L.lo = lo; L.hi1 = M.G.dim[e1] - himargin; L.hi2 = M.G.dim[e2] - himargin;
+        if (e1 == 0 && lo > 1) {
+            if (!M.slab.lo_face) L.lo1 = lo - 1;
+            if (!M.slab.hi_face) L.hi1 = M.G.dim[0] - himargin + 1;
+        }
+    }
+    bool add_mirror(FaceBatch &B, int field, int level, int d, const MirrorOps &ops, int lo, int himargin) const
+    {
         FaceLoop &L = B.loop[B.count];
-        L.kind = 0; L.d = d; L.n = 0; L.lo = lo; L.hi1 = M.G.dim[e1] - himargin; L.hi2 = M.G.dim[e2] - himargin;
+        L.kind = 0; L.d = d; L.n = 0;
+        set_ranges(L, d, lo, himargin);
         L.field = field; L.level = level; L.lv0 = L.lv1 = 0; L.ops = ops;
-        if (L.hi1 <= lo || L.hi2 <= lo) return false;
+        if (L.hi1 <= L.lo1 || L.hi2 <= L.lo) return false;
         ++B.count;
         return true;
     }
     bool add_equation(FaceBatch &B, const DevEq &eq, int lv0, int lv1, int d, int n, int lo, int himargin) const
     {
-        const Model &M = R.M;
-        const int e1 = d == 0 ? 1 : 0, e2 = d == 2 ? 1 : 2;
         FaceLoop &L = B.loop[B.count];
-        L.kind = 1; L.d = d; L.n = n; L.lo = lo; L.hi1 = M.G.dim[e1] - himargin; L.hi2 = M.G.dim[e2] - himargin;
+        L.kind = 1; L.d = d; L.n = n;
+        set_ranges(L, d, lo, himargin);
         L.field = 0; L.level = 0; L.lv0 = lv0; L.lv1 = lv1; L.eq = eq; L.ops.count = 0;
-        if (L.hi1 <= lo || L.hi2 <= lo) return false;
+        if (L.hi1 <= L.lo1 || L.hi2 <= L.lo) return false;
         ++B.count;
         return true;
+    }
+    // x-face loops exist only where the slab end is a physical face
+    bool face_present(int d, int side) const
+    {
+        return d != 0 || (side == 0 ? R.M.slab.lo_face : R.M.slab.hi_face);
     }
     // low and high side of one face pair never touch the same cells once the grid is this large
     bool sides_independent() const
     {
         const Model &M = R.M;
+        if (M.slab.nranks > 1) return false;   // slabs: keep the reference's loop order literally
         for (int d = 0; d < 3; ++d)
             if (M.G.dim[d] < 4 * M.m + 6) return false;
         return true;
@@ -305,6 +382,7 @@ struct Stepper {
                 for (int side = 0; side < 2; ++side) {
                     tmp.count = 0;
                     bool ok = false;
+                    if (!face_present(d, side)) continue;
                     if (fi < 3 && fi == d) {
                         // own-axis normal stress (opesci/fields.py:355-381), ranges [0,dim)
                         MirrorOps ops;
@@ -363,6 +441,7 @@ struct Stepper {
             for (int si = 0; si < 3; ++si) {
                 const int a = seq[si];
                 for (int side = 0; side < 2; ++side) {
+                    if (!face_present(d, side)) continue;
                     if (M.p.free_surface == 1) {
                         int n;
                         if (a == d) n = side == 0 ? m - 1 : M.G.dim[d] - m - 1;
@@ -482,7 +561,7 @@ int setup_fused(Run &R)
     R.fused = false;
     if (p.kind != OPESCI_KIND_STAGGERED_ELASTIC || p.is_double || p.so > 4 || (p.flags & OPESCI_FORCE_UNFUSED)) return 0;
     for (int d = 0; d < 3; ++d)
-        if (p.dim[d] < 6 * M.m + 4) return 0;   // no deep interior worth fusing
+        if (M.G.dim[d] < 6 * M.m + 4) return 0;   // no deep interior worth fusing
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -494,7 +573,7 @@ int setup_fused(Run &R)
     const int m = M.m;
     const int VZ = m == 1 ? FusedCfg<1>::VZ : FusedCfg<2>::VZ, VY = 16 + 2 * m;
     for (int f = 0; f < 3; ++f) {
-        cuuint64_t gdim[3] = {(cuuint64_t)p.dim[2], (cuuint64_t)p.dim[1], (cuuint64_t)p.dim[0] * p.nlevels};
+        cuuint64_t gdim[3] = {(cuuint64_t)p.dim[2], (cuuint64_t)p.dim[1], (cuuint64_t)M.G.dim[0] * p.nlevels};
         cuuint64_t gstride[2] = {(cuuint64_t)M.G.s[1] * 4, (cuuint64_t)M.G.s[0] * 4};
         cuuint32_t box[3] = {(cuuint32_t)VZ, (cuuint32_t)VY, 1};
         cuuint32_t estr[3] = {1, 1, 1};
@@ -511,7 +590,7 @@ int setup_fused(Run &R)
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
     const int CZ = m == 1 ? FusedCfg<1>::CZ : FusedCfg<2>::CZ, CY = 16 - 2 * m;
     const long long tiles = (long long)((p.dim[2] - 2 * m + CZ - 1) / CZ) * ((p.dim[1] - 2 * m + CY - 1) / CY);
-    const int nx = p.dim[0] - 2 * m;
+    const int nx = M.G.dim[0] - 2 * m;
     double best = -1.0;
     for (int nc = 1; nc <= 16; ++nc) {
         const int len = (nx + nc - 1) / nc;
@@ -534,6 +613,9 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     for (int f = 0; f < p.nfields; ++f) {
         Range3 rg;
         for (int d = 0; d < 3; ++d) { rg.lo[d] = p.fields[f].lo[d]; rg.hi[d] = p.fields[f].hi[d]; }
+        // global x range -> planes stored by this rank (local index = global - L0; tables are pre-shifted)
+        rg.lo[0] = (rg.lo[0] > M.slab.L0 ? rg.lo[0] : M.slab.L0) - M.slab.L0;
+        rg.hi[0] = (rg.hi[0] < M.slab.L1 ? rg.hi[0] : M.slab.L1) - M.slab.L0;
         if (rg.hi[0] <= rg.lo[0] || rg.hi[1] <= rg.lo[1] || rg.hi[2] <= rg.lo[2]) continue;
         dim3 blk(64, 4);
         dim3 grid((rg.hi[2] - rg.lo[2] + blk.x - 1) / blk.x, (rg.hi[1] - rg.lo[1] + blk.y - 1) / blk.y, rg.hi[0] - rg.lo[0]);
@@ -548,6 +630,27 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     } else {
         S.template acoustic<SO, T, ARITH>(0, 0, 1, true);
     }
+    const bool slabs = M.slab.nranks > 1;
+    // halo refresh: all fields, one time level, H planes per inner side (contiguous blocks)
+    auto exchange = [&](int level) -> int {
+        const OpesciSlab &sl = M.slab;
+        const size_t plane = (size_t)M.G.s[0], nel = (size_t)sl.halo * plane;
+        NCCL_OK(g_nccl.GroupStart());
+        for (int f = 0; f < p.nfields; ++f) {
+            T *base = (T *)R.dev[f] + (size_t)level * M.G.level;
+            if (!sl.lo_face) {
+                NCCL_OK(g_nccl.Send(base + (size_t)(sl.X0 - sl.L0) * plane, nel * sizeof(T), ncclUint8, sl.rank - 1, g_nccl.comm, st));
+                NCCL_OK(g_nccl.Recv(base, nel * sizeof(T), ncclUint8, sl.rank - 1, g_nccl.comm, st));
+            }
+            if (!sl.hi_face) {
+                NCCL_OK(g_nccl.Send(base + (size_t)(sl.X1 - sl.halo - sl.L0) * plane, nel * sizeof(T), ncclUint8, sl.rank + 1, g_nccl.comm, st));
+                NCCL_OK(g_nccl.Recv(base + (size_t)(sl.X1 - sl.L0) * plane, nel * sizeof(T), ncclUint8, sl.rank + 1, g_nccl.comm, st));
+            }
+        }
+        NCCL_OK(g_nccl.GroupEnd());
+        return 0;
+    };
+    if (slabs && exchange(0)) return 1;
     CUDA_OK(cudaStreamSynchronize(st));
     if (S.err != cudaSuccess) return fail("kernel launch failed during initialisation: %s", cudaGetErrorString(S.err));
 
@@ -555,7 +658,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     CUDA_OK(cudaEventCreate(&e0));
     CUDA_OK(cudaEventCreate(&e1));
     const int nsteps = p.ntsteps;
-    const bool use_graph = !(p.flags & OPESCI_NO_CUDA_GRAPH) && nsteps >= 2 * period;
+    const bool use_graph = !(p.flags & OPESCI_NO_CUDA_GRAPH) && nsteps >= 2 * period && !slabs;
     long long per_period = 0;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
@@ -585,6 +688,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
             } else {
                 if (staggered) S.template staggered_step<SO, T, ARITH>(ti);
                 else S.template acoustic_step<SO, T, ARITH>(ti);
+                if (slabs && exchange((ti + 1) % period)) return 1;   // level t1 of this step
                 ++ti;
             }
         }
@@ -713,7 +817,7 @@ int upload_programs(Run &R)
             dst.n_tables = src.n_tables;
             for (int t = 0; t < src.n_tables; ++t) {
                 dst.table_axis[t] = src.table_axis[t];
-                dst.table[t] = R.d_tables + M.table_off[f][w][t];
+                dst.table[t] = R.d_tables + M.table_off[f][w][t] + (src.table_axis[t] == 0 ? M.slab.L0 : 0);
             }
             for (int i = 0; i < src.n_instr; ++i) dst.instr[i] = src.instr[i];
         }
@@ -739,9 +843,15 @@ template <typename T> int l2_sums(Run &R, const void *const *level_base_dev, dou
     size_t max_blocks = 1;
     dim3 blk(64, 4);
     std::vector<dim3> grids(M.p.nfields);
+    std::vector<Range3> ranges(M.p.nfields);
     for (int f = 0; f < M.p.nfields; ++f) {
         const OpesciFieldSpec &fs = M.p.fields[f];
-        const int nz = fs.l2_hi[2] - fs.l2_lo[2], ny = fs.l2_hi[1] - fs.l2_lo[1], nx = fs.l2_hi[0] - fs.l2_lo[0];
+        Range3 &rg = ranges[f];
+        for (int d = 0; d < 3; ++d) { rg.lo[d] = fs.l2_lo[d]; rg.hi[d] = fs.l2_hi[d]; }
+        // every rank sums over the planes it OWNS (global range clipped), in local indices
+        rg.lo[0] = (rg.lo[0] > M.slab.own_lo ? rg.lo[0] : M.slab.own_lo) - M.slab.L0;
+        rg.hi[0] = (rg.hi[0] < M.slab.own_hi ? rg.hi[0] : M.slab.own_hi) - M.slab.L0;
+        const int nz = rg.hi[2] - rg.lo[2], ny = rg.hi[1] - rg.lo[1], nx = rg.hi[0] - rg.lo[0];
         grids[f] = dim3(nz > 0 ? (nz + blk.x - 1) / blk.x : 0, ny > 0 ? (ny + blk.y - 1) / blk.y : 0, nx > 0 ? nx : 0);
         const size_t nb = (size_t)grids[f].x * grids[f].y * grids[f].z;
         if (nb > max_blocks) max_blocks = nb;
@@ -750,10 +860,12 @@ template <typename T> int l2_sums(Run &R, const void *const *level_base_dev, dou
     for (int f = 0; f < M.p.nfields; ++f) {
         const size_t nb = (size_t)grids[f].x * grids[f].y * grids[f].z;
         if (nb == 0) continue;
-        Range3 rg;
-        for (int d = 0; d < 3; ++d) { rg.lo[d] = M.p.fields[f].l2_lo[d]; rg.hi[d] = M.p.fields[f].l2_hi[d]; }
-        l2_partial<T><<<grids[f], blk, 0, st>>>((const T *)level_base_dev[f], M.G, rg, R.d_prog + 2 * f + 1, d_partial);
+        l2_partial<T><<<grids[f], blk, 0, st>>>((const T *)level_base_dev[f], M.G, ranges[f], R.d_prog + 2 * f + 1, d_partial);
         l2_final<<<1, 1024, 0, st>>>(d_partial, nb, d_out + f);
+    }
+    if (M.slab.nranks > 1) {
+        // sum of the per-slab partial sums (ncclAllReduce of 9 doubles)
+        NCCL_OK(g_nccl.AllReduce(d_out, d_out, OPESCI_MAX_FIELDS, ncclFloat64, ncclSum, g_nccl.comm, st));
     }
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpy(sums, d_out, OPESCI_MAX_FIELDS * sizeof(double), cudaMemcpyDeviceToHost));
@@ -783,7 +895,7 @@ int convergence_sums(OpesciGrid *grid, double *sums, Model **model_out)
     const size_t esz = M.p.is_double ? 8 : 4;
     const size_t lvl_bytes = (size_t)M.G.level * esz;
     const size_t host_row = (size_t)M.p.dim[2] * esz, dev_row = (size_t)M.G.s[1] * esz;
-    const size_t rows = (size_t)M.p.dim[0] * M.p.dim[1];
+    const size_t rows = (size_t)M.G.dim[0] * M.p.dim[1];
     const size_t host_lvl_bytes = rows * host_row;
     for (int f = 0; f < M.p.nfields; ++f) {
         if (!tmp) {
@@ -823,11 +935,19 @@ int opesci_b200_configure(const OpesciB200Params *params)
     if (params->so < 2 || params->so > 12 || (params->so & 1)) return fail("opesci_b200_configure: so must be even, 2..12");
     for (int d = 0; d < 3; ++d)
         if (params->dim[d] < 2 * (params->so / 2) + 1) return fail("opesci_b200_configure: grid too small for the stencil");
+    if (params->slab_nranks > 1 && params->kind != OPESCI_KIND_STAGGERED_ELASTIC)
+        return fail("opesci_b200_configure: slab decomposition is implemented for the staggered elastic model");
     Model &M = g_model;
     M = Model();
     M.p = *params;
     M.m = params->so / 2;
+    const int nranks = params->slab_nranks > 1 ? params->slab_nranks : 1;
+    if (opesci_slab_make(&M.slab, nranks > 1 ? params->slab_rank : 0, nranks, params->dim[0], M.m, OPESCI_SLAB_HALO))
+        return fail("opesci_b200_configure: slabs thinner than the halo (or so > 4 with slabs): use fewer ranks");
+    if (nranks > 1 && (!g_nccl.comm || g_nccl.nranks != nranks || g_nccl.rank != params->slab_rank))
+        return fail("opesci_b200_configure: slab_nranks > 1 needs opesci_b200_comm_init with the same rank / size first");
     for (int d = 0; d < 3; ++d) M.G.dim[d] = params->dim[d];
+    M.G.dim[0] = M.slab.L1 - M.slab.L0;   // local planes; p.dim[0] stays the global dim1
     M.G.m = M.m;
     // device rows are padded to a multiple of 32 elements (TMA needs 16-B row strides; 128-B rows
     // keep tiles sector-aligned); the host arrays keep the reference's dense layout
@@ -835,7 +955,7 @@ int opesci_b200_configure(const OpesciB200Params *params)
     M.G.s[0] = (long long)params->dim[1] * pitch;
     M.G.s[1] = pitch;
     M.G.s[2] = 1;
-    M.G.level = (long long)params->dim[0] * params->dim[1] * pitch;
+    M.G.level = (long long)M.G.dim[0] * params->dim[1] * pitch;
     memcpy(M.sc.sn, params->c_stress_normal, sizeof M.sc.sn);
     memcpy(M.sc.ss, params->c_stress_shear, sizeof M.sc.ss);
     memcpy(M.sc.v, params->c_velocity, sizeof M.sc.v);
@@ -896,7 +1016,7 @@ int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
     const OpesciB200Params &p = R->M.p;
     const size_t esz = p.is_double ? 8 : 4;
     R->bytes_per_field = (size_t)R->M.G.level * p.nlevels * esz;
-    R->host_bytes_per_field = (size_t)p.dim[0] * p.dim[1] * p.dim[2] * p.nlevels * esz;
+    R->host_bytes_per_field = (size_t)R->M.G.dim[0] * p.dim[1] * p.dim[2] * p.nlevels * esz;
     cudaStream_t st;
     if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { release(R); return fail("cudaStreamCreate failed"); }
     auto bail = [&](int rc) { cudaStreamDestroy(st); release(R); return rc; };
@@ -924,7 +1044,7 @@ int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
             }
             // dense host rows (reference layout [tp][dim1][dim2][dim3]) <- pitched device rows
             if (cudaMemcpy2DAsync(R->host[f], (size_t)p.dim[2] * esz, R->dev[f], (size_t)R->M.G.s[1] * esz, (size_t)p.dim[2] * esz,
-                                  (size_t)p.nlevels * p.dim[0] * p.dim[1], cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                                  (size_t)p.nlevels * R->M.G.dim[0] * p.dim[1], cudaMemcpyDeviceToHost, st) != cudaSuccess)
                 return bail(fail("opesci_execute: D2H copy failed"));
         }
         if (cudaStreamSynchronize(st) != cudaSuccess) return bail(fail("opesci_execute: D2H copy failed (%s)", cudaGetErrorString(cudaGetLastError())));
@@ -998,6 +1118,38 @@ int opesci_b200_time_kernels(OpesciGrid *grid, int reps, double *out_ms)
     if (R->M.p.is_double)
         return fast ? time_kernels_so<double, OPESCI_ARITH_FAST>(*R, reps, out_ms) : time_kernels_so<double, OPESCI_ARITH_REFERENCE>(*R, reps, out_ms);
     return fast ? time_kernels_so<float, OPESCI_ARITH_FAST>(*R, reps, out_ms) : time_kernels_so<float, OPESCI_ARITH_REFERENCE>(*R, reps, out_ms);
+}
+
+int opesci_b200_comm_unique_id(void *out_id, int nbytes)
+{
+    if (nbytes < (int)sizeof(ncclUniqueId)) return fail("opesci_b200_comm_unique_id: buffer too small");
+    if (nccl_bind()) return 1;
+    ncclUniqueId id;
+    NCCL_OK(g_nccl.GetUniqueId(&id));
+    memcpy(out_id, &id, sizeof id);
+    return 0;
+}
+
+int opesci_b200_comm_init(int rank, int nranks, const void *id_bytes, int nbytes)
+{
+    if (nbytes < (int)sizeof(ncclUniqueId) || nranks < 1 || rank < 0 || rank >= nranks) return fail("opesci_b200_comm_init: bad arguments");
+    if (nccl_bind()) return 1;
+    if (g_nccl.comm) { g_nccl.CommDestroy(g_nccl.comm); g_nccl.comm = nullptr; }
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof id);
+    NCCL_OK(g_nccl.CommInitRank(&g_nccl.comm, nranks, id, rank));
+    g_nccl.rank = rank;
+    g_nccl.nranks = nranks;
+    return 0;
+}
+
+int opesci_b200_comm_finalize(void)
+{
+    if (g_nccl.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g_nccl.comm);
+    g_nccl.comm = nullptr;
+    g_nccl.rank = 0;
+    g_nccl.nranks = 1;
+    return 0;
 }
 
 int opesci_b200_last_timing(double *loop_seconds, double *points_per_step, int64_t *kernel_launches)

@@ -34,6 +34,8 @@
 #include <string.h>
 
 #include "../include/opesci_b200.h"
+#include "../include/opesci_slab.h"
+#include "opesci_oracle_slab.h"
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -66,11 +68,21 @@ typedef struct {
     Equation lev_vel_eq[3][3][2];    /* [face axis d][velocity a][side] */
     double *tables;         /* private copy of every 1-D table */
     int configured;
+    OpesciSlab slab;        /* x-slab of this rank; p.dim[0] holds the LOCAL plane count after configure */
+    int gdim1;              /* global dim1 */
 } Model;
 
 static Model g_model;
 static char g_err[512] = "";
 static double g_loop_seconds = 0.0;
+static opesci_oracle_exchange_fn g_exchange = NULL;
+static void *g_exchange_user = NULL;
+
+void opesci_oracle_set_exchange(opesci_oracle_exchange_fn fn, void *user)
+{
+    g_exchange = fn;
+    g_exchange_user = user;
+}
 
 static int fail(const char *msg)
 {
@@ -272,10 +284,18 @@ int opesci_b200_configure(const OpesciB200Params *params)
     memset(M, 0, sizeof *M);
     M->p = *params;
     M->m = params->so / 2;
+    M->gdim1 = params->dim[0];
+    {
+        const int nr = params->slab_nranks > 1 ? params->slab_nranks : 1;
+        if (opesci_slab_make(&M->slab, nr > 1 ? params->slab_rank : 0, nr, params->dim[0], M->m, OPESCI_SLAB_HALO))
+            return fail("oracle: slabs thinner than the halo");
+        if (nr > 1 && !g_exchange) return fail("oracle: slab_nranks > 1 needs opesci_oracle_set_exchange first");
+        M->p.dim[0] = M->slab.L1 - M->slab.L0;   /* every loop below runs on the local slab */
+    }
     M->s[0] = (long)params->dim[1] * params->dim[2];
     M->s[1] = params->dim[2];
     M->s[2] = 1;
-    M->level_elems = (size_t)params->dim[0] * params->dim[1] * params->dim[2];
+    M->level_elems = (size_t)M->p.dim[0] * params->dim[1] * params->dim[2];
     /* deep-copy tables */
     size_t total = 0;
     for (int f = 0; f < params->nfields; ++f)
@@ -291,10 +311,20 @@ int opesci_b200_configure(const OpesciB200Params *params)
             for (int t = 0; t < pr->n_tables; ++t) {
                 size_t n = (size_t)params->dim[pr->table_axis[t]];
                 memcpy(M->tables + pos, pr->table[t], n * sizeof(double));
-                pr->table[t] = M->tables + pos;
+                /* x tables are indexed with local plane numbers: shift by the slab origin */
+                pr->table[t] = M->tables + pos + (pr->table_axis[t] == 0 ? M->slab.L0 : 0);
                 pos += n;
             }
         }
+    for (int f = 0; f < params->nfields; ++f) {
+        OpesciFieldSpec *fs = &M->p.fields[f];
+        const OpesciSlab *sl = &M->slab;
+        /* init on every stored plane, L2 on the owned planes; global -> local x */
+        fs->lo[0] = (fs->lo[0] > sl->L0 ? fs->lo[0] : sl->L0) - sl->L0;
+        fs->hi[0] = (fs->hi[0] < sl->L1 ? fs->hi[0] : sl->L1) - sl->L0;
+        fs->l2_lo[0] = (fs->l2_lo[0] > sl->own_lo ? fs->l2_lo[0] : sl->own_lo) - sl->L0;
+        fs->l2_hi[0] = (fs->l2_hi[0] < sl->own_hi ? fs->l2_hi[0] : sl->own_hi) - sl->L0;
+    }
     if (params->kind == OPESCI_KIND_STAGGERED_ELASTIC) {
         if (params->nfields != 9 || params->nlevels != 2) return fail("staggered: need 9 fields, 2 levels");
         build_staggered(M);
@@ -394,6 +424,10 @@ int opesci_free(OpesciGrid *grid)
     return 0;
 }
 
+int opesci_b200_comm_unique_id(void *out_id, int nbytes) { (void)out_id; (void)nbytes; return fail("oracle: no NCCL; use opesci_oracle_set_exchange"); }
+int opesci_b200_comm_init(int rank, int nranks, const void *id, int nbytes) { (void)rank; (void)nranks; (void)id; (void)nbytes; return fail("oracle: no NCCL; use opesci_oracle_set_exchange"); }
+int opesci_b200_comm_finalize(void) { return 0; }
+
 int opesci_b200_time_kernels(OpesciGrid *grid, int reps, double *out_ms)
 {
     (void)grid; (void)reps; (void)out_ms;
@@ -405,7 +439,7 @@ int opesci_b200_last_timing(double *loop_seconds, double *points_per_step, int64
     const Model *M = &g_model;
     if (loop_seconds) *loop_seconds = g_loop_seconds;
     if (points_per_step)
-        *points_per_step = (double)(M->p.dim[0] - 2 * M->m) * (M->p.dim[1] - 2 * M->m) * (M->p.dim[2] - 2 * M->m);
+        *points_per_step = (double)(M->gdim1 - 2 * M->m) * (M->p.dim[1] - 2 * M->m) * (M->p.dim[2] - 2 * M->m);
     if (kernel_launches) *kernel_launches = 0;
     return 0;
 }

@@ -1,0 +1,59 @@
+"""GPU, 2 ranks over NCCL: the slab-decomposed CUDA run equals the single-GPU run bit for bit."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from common import ROOT, bits, fields_of, make_grid
+from opesci_fd_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
+@pytest.mark.parametrize("arith", [abi.ARITH_REFERENCE, abi.ARITH_FAST])
+def test_two_gpu_slabs_equal_single_gpu(arith, cuda_lib, tmp_path):
+    cfg = dict(kind="eigenwave3d", so=4, grid_size=[96, 70, 130], dt=0.002, steps=9, double=False,
+               domain=[1.0, 0.9, 0.8], rho=1.2, vp=1.6, vs=0.8)
+    single = make_grid(cfg, flags=arith | abi.HOST_MIRROR_FULL)
+    single.run(library=cuda_lib)
+    ref = fields_of(single)
+    ref_l2 = np.array(single.convergence_f64())
+    single.free()
+    os.environ["OPESCI_TEST_FLAGS"] = str(arith | abi.HOST_MIRROR_FULL)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "slab_worker.py"), str(tmp_path), json.dumps(cfg), "cuda"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    covered = 0
+    for r in range(2):
+        z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        L0, own_lo, own_hi = int(z["L0"]), int(z["own_lo"]), int(z["own_hi"])
+        mine = np.ascontiguousarray(z["fields"][:, :, own_lo - L0:own_hi - L0])
+        want = np.ascontiguousarray(ref[:, :, own_lo:own_hi])
+        assert int((bits(mine) != bits(want)).sum()) == 0, "rank %d differs from the single-GPU run" % r
+        covered += own_hi - own_lo
+        # every rank holds the all-reduced global norms
+        np.testing.assert_allclose(z["l2"], ref_l2, rtol=1e-12)
+    assert covered == ref.shape[2]
