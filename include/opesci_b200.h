@@ -24,6 +24,7 @@
 #ifndef OPESCI_B200_H
 #define OPESCI_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -180,6 +181,12 @@ int opesci_b200_last_timing(double *loop_seconds, double *points_per_step, int64
  * out_ms[0] = stress (or fused stress+velocity) kernel, out_ms[1] = velocity kernel (0 if fused),
  * out_ms[2] = all ghost-cell loops of one step.  Advances the fields; call it last. */
 int opesci_b200_time_kernels(OpesciGrid *grid, int reps, double *out_ms);
+/* Host result arrays (OPESCI_HOST_MIRROR_FULL) come from a process-wide pool of page-locked blocks that
+ * outlives opesci_free; reserve_host pre-fills it with `count` blocks of `bytes_per_array`
+ * (page-locking tens of GB takes far longer than copying them), release_host frees the unused blocks. */
+int opesci_b200_reserve_host(size_t bytes_per_array, int count);
+int opesci_b200_release_host(void);
+
 /* ---- multi-GPU: x-slab decomposition (no reference counterpart: the reference is OpenMP only) ----
  * One process per GPU.  dim1 is split into contiguous slabs; every rank keeps OPESCI_SLAB_HALO planes
  * of all fields on each inner side, computes a whole time step on its local slab (x-face loops only

@@ -86,6 +86,7 @@ EXPORTED_SYMBOLS = [
     "opesci_b200_last_error", "opesci_b200_convergence_f64", "opesci_b200_last_timing",
     "opesci_b200_is_cuda", "opesci_b200_time_kernels",
     "opesci_b200_comm_unique_id", "opesci_b200_comm_init", "opesci_b200_comm_finalize",
+    "opesci_b200_reserve_host", "opesci_b200_release_host",
 ]
 SLAB_HALO = 8
 COMM_ID_BYTES = 128
@@ -113,6 +114,11 @@ def bind(lib):
     if hasattr(lib, "opesci_b200_time_kernels"):
         lib.opesci_b200_time_kernels.argtypes = [POINTER(OpesciGrid), ctypes.c_int, POINTER(c_double)]
         lib.opesci_b200_time_kernels.restype = ctypes.c_int
+    if hasattr(lib, "opesci_b200_reserve_host"):
+        lib.opesci_b200_reserve_host.argtypes = [ctypes.c_size_t, ctypes.c_int]
+        lib.opesci_b200_reserve_host.restype = ctypes.c_int
+        lib.opesci_b200_release_host.argtypes = []
+        lib.opesci_b200_release_host.restype = ctypes.c_int
     if hasattr(lib, "opesci_b200_comm_init"):
         lib.opesci_b200_comm_unique_id.argtypes = [c_void_p, ctypes.c_int]
         lib.opesci_b200_comm_unique_id.restype = ctypes.c_int

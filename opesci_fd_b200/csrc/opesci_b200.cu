@@ -134,6 +134,38 @@ std::mutex g_mu;
 double g_loop_seconds = 0.0;
 long long g_launches = 0;
 
+// ------------------------------------------------------------------ pinned host pool
+// The reference ABI hands back host arrays.  Page-locking 80 GB costs tens of seconds, far more than
+// the copy itself, so result arrays come from a process-wide pool of pinned blocks that survives
+// opesci_free (opesci_b200_reserve_host pre-fills it, opesci_b200_release_host frees it).
+struct HostBlock { void *ptr; size_t bytes; bool in_use; bool pinned; };
+std::vector<HostBlock> g_pool;
+std::mutex g_pool_mu;
+
+void *pool_alloc(size_t bytes, bool *pinned)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_pool.size(); ++i)
+        if (!g_pool[i].in_use && g_pool[i].bytes >= bytes && (best < 0 || g_pool[i].bytes < g_pool[best].bytes)) best = i;
+    if (best >= 0) { g_pool[best].in_use = true; *pinned = g_pool[best].pinned; return g_pool[best].ptr; }
+    HostBlock b{nullptr, bytes, true, true};
+    if (cudaMallocHost(&b.ptr, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        b.pinned = false;
+        if (posix_memalign(&b.ptr, 4096, bytes) != 0) return nullptr;
+    }
+    g_pool.push_back(b);
+    *pinned = b.pinned;
+    return b.ptr;
+}
+void pool_release(void *ptr)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (auto &b : g_pool)
+        if (b.ptr == ptr) b.in_use = false;
+}
+
 // ------------------------------------------------------------------ model construction
 void push(DevEq &eq, int kind, int field, int level, long long off, float coef)
 {
@@ -790,10 +822,7 @@ void release(Run *R)
 {
     for (int f = 0; f < OPESCI_MAX_FIELDS; ++f) {
         if (R->dev[f]) cudaFree(R->dev[f]);
-        if (R->host[f]) {
-            if (R->host_pinned) cudaFreeHost(R->host[f]);
-            else free(R->host[f]);
-        }
+        if (R->host[f]) pool_release(R->host[f]);
     }
     if (R->d_tables) cudaFree(R->d_tables);
     if (R->d_prog) cudaFree(R->d_prog);
@@ -1034,14 +1063,11 @@ int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
     const int mirror = p.flags & OPESCI_HOST_MIRROR_MASK;
     if (mirror == OPESCI_HOST_MIRROR_FULL) {
         for (int f = 0; f < p.nfields; ++f) {
-            // pinned host arrays: the D2H copy runs at PCIe speed
-            if (cudaMallocHost(&R->host[f], R->host_bytes_per_field) == cudaSuccess) {
-                R->host_pinned = true;
-            } else {
-                cudaGetLastError();
-                if (R->host_pinned) return bail(fail("opesci_execute: pinned host allocation failed"));
-                if (posix_memalign(&R->host[f], 4096, R->host_bytes_per_field) != 0) return bail(fail("opesci_execute: host allocation failed"));
-            }
+            // pinned host arrays from the pool: the D2H copy runs at PCIe speed
+            bool pinned = false;
+            R->host[f] = pool_alloc(R->host_bytes_per_field, &pinned);
+            if (!R->host[f]) return bail(fail("opesci_execute: host allocation failed"));
+            R->host_pinned = pinned;
             // dense host rows (reference layout [tp][dim1][dim2][dim3]) <- pitched device rows
             if (cudaMemcpy2DAsync(R->host[f], (size_t)p.dim[2] * esz, R->dev[f], (size_t)R->M.G.s[1] * esz, (size_t)p.dim[2] * esz,
                                   (size_t)p.nlevels * R->M.G.dim[0] * p.dim[1], cudaMemcpyDeviceToHost, st) != cudaSuccess)
@@ -1149,6 +1175,32 @@ int opesci_b200_comm_finalize(void)
     g_nccl.comm = nullptr;
     g_nccl.rank = 0;
     g_nccl.nranks = 1;
+    return 0;
+}
+
+int opesci_b200_reserve_host(size_t bytes_per_array, int count)
+{
+    std::vector<void *> got;
+    for (int i = 0; i < count; ++i) {
+        bool pinned = false;
+        void *p = pool_alloc(bytes_per_array, &pinned);
+        if (!p) { for (void *q : got) pool_release(q); return fail("opesci_b200_reserve_host: allocation failed"); }
+        got.push_back(p);
+    }
+    for (void *q : got) pool_release(q);
+    return 0;
+}
+
+int opesci_b200_release_host(void)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    std::vector<HostBlock> keep;
+    for (auto &b : g_pool) {
+        if (b.in_use) { keep.push_back(b); continue; }
+        if (b.pinned) cudaFreeHost(b.ptr);
+        else free(b.ptr);
+    }
+    g_pool.swap(keep);
     return 0;
 }
 

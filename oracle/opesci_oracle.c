@@ -427,6 +427,8 @@ int opesci_free(OpesciGrid *grid)
 int opesci_b200_comm_unique_id(void *out_id, int nbytes) { (void)out_id; (void)nbytes; return fail("oracle: no NCCL; use opesci_oracle_set_exchange"); }
 int opesci_b200_comm_init(int rank, int nranks, const void *id, int nbytes) { (void)rank; (void)nranks; (void)id; (void)nbytes; return fail("oracle: no NCCL; use opesci_oracle_set_exchange"); }
 int opesci_b200_comm_finalize(void) { return 0; }
+int opesci_b200_reserve_host(size_t bytes_per_array, int count) { (void)bytes_per_array; (void)count; return 0; }
+int opesci_b200_release_host(void) { return 0; }
 
 int opesci_b200_time_kernels(OpesciGrid *grid, int reps, double *out_ms)
 {
