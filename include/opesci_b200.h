@@ -111,7 +111,9 @@ enum {
     OPESCI_HOST_MIRROR_NONE = 1 << 4,   /* grid->field[] = DEVICE pointers; nothing copied back */
     OPESCI_HOST_MIRROR_MASK = 0x30,
     OPESCI_NO_CUDA_GRAPH = 1 << 8,
-    OPESCI_FORCE_UNFUSED = 1 << 9       /* two-pass stress / velocity kernels (diagnostic) */
+    OPESCI_FORCE_UNFUSED = 1 << 9,      /* two-pass stress / velocity kernels (diagnostic) */
+    OPESCI_OVERLAP = 1 << 10            /* experimental: run the ghost loops of step n-1 concurrently with the tiles of
+                                         * step n that cannot see them (bit-identical; no gain measured on B200) */
 };
 
 typedef struct OpesciB200Params {

@@ -26,6 +26,7 @@ HOST_MIRROR_FULL = 0 << 4
 HOST_MIRROR_NONE = 1 << 4
 NO_CUDA_GRAPH = 1 << 8
 FORCE_UNFUSED = 1 << 9
+OVERLAP = 1 << 10
 
 FS_NONE, FS_LEVANDER, FS_ROBERTSSON = 0, 1, 2
 

@@ -12,7 +12,7 @@
 // stresses are stored for the whole interior [m, dim-m)^3, velocities only for the "deep"
 // interior [2m+1, dim-2m-1)^3 whose stress stencil touches cells no boundary loop rewrites
 // (staggeredgrid.py:750-813 writes only cells with an index <= m or >= dim-m-1).  The thin shell
-// that is left is updated after the stress ghost loops by velocity_box (kernels.cuh), so the
+// that is left is updated after the stress ghost loops by velocity_shell_kernel (below), so the
 // per-step order stress -> stress BC -> velocity -> velocity BC of
 // opesci/templates/staggered3d_tmpl.py:40-58 is preserved cell for cell.
 //
@@ -116,6 +116,11 @@ struct FusedArgs {
     StaggeredCoefs C;
     int t0, t1;
     int xchunk;       // planes per x-chunk
+    // Tile subset of this launch.  The tiles inside the box [box_lo, box_hi) (tile_y, tile_z, chunk)
+    // neither read nor write any cell the ghost-cell loops / shell update of the PREVIOUS step touch,
+    // so they can run concurrently with those loops; the remaining tiles run afterwards.
+    int mode;         // 0: every tile, 1: only tiles inside the box, 2: only tiles outside the box
+    int box_lo[3], box_hi[3];
 };
 
 // six consecutive floats p[-2..3] as three aligned 8-byte loads (p must be 8-byte aligned)
@@ -184,6 +189,11 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 
     const GridGeom &G = A.G;
     const int tid = threadIdx.x;
+    if (A.mode != 0) {
+        const bool inside = (int)blockIdx.y >= A.box_lo[0] && (int)blockIdx.y < A.box_hi[0] && (int)blockIdx.x >= A.box_lo[1] &&
+                            (int)blockIdx.x < A.box_hi[1] && (int)blockIdx.z >= A.box_lo[2] && (int)blockIdx.z < A.box_hi[2];
+        if ((A.mode == 1) != inside) return;
+    }
     const int tz = 2 * (tid % (K::EZ / 2)), ty = tid / (K::EZ / 2);          // lane 0 sits at tz, lane 1 at tz+1
     const int ye = blockIdx.y * K::CY + ty, ze = blockIdx.x * K::CZ + tz;   // global coords of lane 0
     const int xa = M + blockIdx.z * A.xchunk;
@@ -506,47 +516,6 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     }
 }
 
-// velocity update on a box of interior points (the shell the fused kernel leaves out), operands
-// from global memory: identical arithmetic to velocity_interior
-template <int SO, typename T, int ARITH>
-__global__ void __launch_bounds__(256)
-velocity_box(FieldPtrs F, GridGeom G, StaggeredCoefs C, int t0, int t1, Range3 R)
-{
-    constexpr int M = SO / 2;
-    const int z = R.lo[2] + blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = R.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
-    const int x = R.lo[0] + blockIdx.z;
-    if (z >= R.hi[2] || y >= R.hi[1]) return;
-    const long long p = (long long)x * G.s[0] + (long long)y * G.s[1] + z;
-    const long long r = (long long)t0 * G.level + p, w = (long long)t1 * G.level + p;
-    const long long st[3] = {G.s[0], G.s[1], 1};
-    const int opnd[3][3] = {{F_TXX, F_TXY, F_TXZ}, {F_TXY, F_TYY, F_TYZ}, {F_TXZ, F_TYZ, F_TZZ}};
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        T *Va = (T *)F.f[F_U + a];
-        if (ARITH == OPESCI_ARITH_REFERENCE) {
-            T acc = 0;
-            bool first = true;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const T *g = (const T *)F.f[opnd[a][d]] + w;
-                if (d == a) window_ref<M, T, true>(acc, first, g, st[d], C.v[a][d]);
-                else window_ref<M, T, false>(acc, first, g, st[d], C.v[a][d]);
-            }
-            Va[w] = add_rn<T>(acc, Va[r]);
-        } else {
-            T acc = 0;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const T *g = (const T *)F.f[opnd[a][d]] + w;
-                acc += (d == a) ? window_fast<M, T, true>(g, st[d], C.v[a][d])
-                                : window_fast<M, T, false>(g, st[d], C.v[a][d]);
-            }
-            Va[w] = Va[r] + acc;
-        }
-    }
-}
-
 // All six shell slabs in one launch: blockIdx.x is a flat block index over the boxes.
 struct ShellBoxes {
     Range3 r[6];
@@ -555,7 +524,7 @@ struct ShellBoxes {
     int start[7];        // prefix sums of the block counts
 };
 template <int SO, typename T, int ARITH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(OPESCI_FACE_THREADS)
 velocity_shell_kernel(FieldPtrs F, GridGeom G, StaggeredCoefs C, int t0, int t1, const __grid_constant__ ShellBoxes B)
 {
     constexpr int M = SO / 2;
@@ -568,7 +537,7 @@ velocity_shell_kernel(FieldPtrs F, GridGeom G, StaggeredCoefs C, int t0, int t1,
     const int bz = rem % B.nbz[b];
     rem /= B.nbz[b];
     const int by = rem % B.nby[b], bx = rem / B.nby[b];
-    const int tw = B.zwide[b] ? 64 : 4, th = 256 / tw;
+    const int tw = B.zwide[b] ? 64 : 4, th = OPESCI_FACE_THREADS / tw;
     const int z = R.lo[2] + bz * tw + (int)(threadIdx.x % tw);
     const int y = R.lo[1] + by * th + (int)(threadIdx.x / tw);
     const int x = R.lo[0] + bx;

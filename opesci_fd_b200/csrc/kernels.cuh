@@ -3,7 +3,7 @@
 // What each kernel replaces in the reference's generated OpenMP C++:
 //   stress_interior<SO,T,ARITH>    stress loop      opesci/staggeredgrid.py:728-737 -> regulargrid.py:566-619
 //   velocity_interior<SO,T,ARITH>  velocity loop    opesci/staggeredgrid.py:739-748
-//   face_mirror<T>, face_equation<T>  the 30+18 (so=4) / 18+18 ghost-cell loops
+//   face_batch<T>                  the 30+18 (so=4) / 18+18 ghost-cell loops, batched
 //                                  opesci/staggeredgrid.py:750-864, opesci/fields.py:192-261, 294-381
 //   acoustic_interior<SO,T,ARITH>  regular-grid update + second initialisation  regulargrid.py:530-564, 592-619
 //   init_field<T>, l2_partial<T>   analytic initialisation / L2 test  staggeredgrid.py:612-659, 892-945
@@ -249,53 +249,11 @@ struct DevEq {
     DevTerm term[OPESCI_MAX_FACE_TERMS];
 };
 
-// One reference loop `for e1 in [lo,hi1) for e2 in [lo,hi2): out[plane n] = sum terms`
-// (Levander loops, always in reference arithmetic: they are O(N^2)).
-template <typename T>
-__global__ void face_equation(FieldPtrs F, GridGeom G, DevEq eq, int lv0, int lv1, int d, int n, int lo, int hi1,
-                              int hi2)
-{
-    const int e1 = (d == 0) ? 1 : 0, e2 = (d == 2) ? 1 : 2;
-    const int j = lo + blockIdx.x * blockDim.x + threadIdx.x;   // along e2 (contiguous unless d == 2)
-    const int i = lo + blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= hi1 || j >= hi2) return;
-    const long long p = (long long)i * G.s[e1] + (long long)j * G.s[e2] + (long long)n * G.s[d];
-    const long long lv[2] = {(long long)lv0 * G.level, (long long)lv1 * G.level};
-    T acc = 0;
-    bool first = true;
-    for (int k = 0; k < eq.nterm; ++k) {
-        const DevTerm t = eq.term[k];
-        const T g = ((const T *)F.f[t.field])[lv[t.level] + p + t.off];
-        T v;
-        if (t.kind == TERM_MUL) v = mul_rn<T>((T)t.coef, g);
-        else if (t.kind == TERM_PLUS) v = g;
-        else v = -g;
-        acc = first ? v : add_rn<T>(acc, v);
-        first = false;
-    }
-    ((T *)F.f[eq.out])[lv[eq.out_level] + p] = acc;
-}
-
 // One reference loop made of plane assignments  field[dst_k] = 0 | -field[src_k]  along axis d.
 struct MirrorOps {
     int count;
     int dst[OPESCI_MAX_M], src[OPESCI_MAX_M];   // plane indices along d; src < 0: assign 0
 };
-template <typename T>
-__global__ void face_mirror(T *__restrict__ A /* level base */, GridGeom G, MirrorOps ops, int d, int lo, int hi1,
-                            int hi2)
-{
-    const int e1 = (d == 0) ? 1 : 0, e2 = (d == 2) ? 1 : 2;
-    const int j = lo + blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = lo + blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= hi1 || j >= hi2) return;
-    const long long q = (long long)i * G.s[e1] + (long long)j * G.s[e2];
-    for (int k = 0; k < ops.count; ++k) {
-        const T v = ops.src[k] < 0 ? (T)0 : -A[q + (long long)ops.src[k] * G.s[d]];
-        A[q + (long long)ops.dst[k] * G.s[d]] = v;
-    }
-}
-
 
 // ---- batched ghost-cell loops -----------------------------------------------------------
 // The reference runs its 48 (so=4) / 36 ghost loops one after the other, each an `omp for`
@@ -318,8 +276,11 @@ struct FaceBatch {
     FaceLoop loop[OPESCI_MAX_BATCH];
 };
 
+// 128-thread blocks with few registers: these loops are meant to run NEXT TO a resident fused_step CTA
+// (512 threads x 112 registers leave 8192 registers per SM), see the pipelined stepping in opesci_b200.cu
+#define OPESCI_FACE_THREADS 128
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(OPESCI_FACE_THREADS)
 face_batch(FieldPtrs F, GridGeom G, const __grid_constant__ FaceBatch B)
 {
     int li = 0;
@@ -331,7 +292,7 @@ face_batch(FieldPtrs F, GridGeom G, const __grid_constant__ FaceBatch B)
     const int d = L.d;
     const int e1 = (d == 0) ? 1 : 0, e2 = (d == 2) ? 1 : 2;
     // threads run along e2 (contiguous z) except on z-faces, where 8 x 32 tiles keep a little locality
-    const int w = (d == 2) ? 8 : 128, h = 256 / w;
+    const int w = (d == 2) ? 8 : 128, h = OPESCI_FACE_THREADS / w;
     const int j = L.lo + bx * w + (int)(threadIdx.x % w);
     const int i = L.lo1 + by * h + (int)(threadIdx.x / w);
     if (i >= L.hi1 || j >= L.hi2) return;

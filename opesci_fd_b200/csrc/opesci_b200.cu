@@ -127,6 +127,8 @@ struct Run {
     bool fused = false;             // fused stress+velocity kernel in use
     CUtensorMap tmap[3];            // U, V, W (both time levels; level selected through the x coordinate)
     int xchunk = 0, nchunks = 1;
+    bool overlap = false;           // ghost loops of step n-1 run concurrently with the independent tiles of step n
+    int box_lo[3] = {0, 0, 0}, box_hi[3] = {0, 0, 0};   // independent tiles (tile_y, tile_z, chunk)
 };
 std::map<void *, Run *> g_runs;
 std::mutex g_mu;
@@ -296,37 +298,6 @@ struct Stepper {
         check();
     }
 
-    // face launch geometry: threads along e2 (contiguous unless d == 2)
-    void face_dims(int d, int lo, int hi1, int hi2, dim3 &grid, dim3 &blk) const
-    {
-        blk = d == 2 ? dim3(8, 32) : dim3(128, 2);
-        const int n2 = hi2 - lo, n1 = hi1 - lo;
-        grid = dim3((n2 + blk.x - 1) / blk.x, (n1 + blk.y - 1) / blk.y);
-    }
-    template <typename T> void mirror(int field, int level, int d, const MirrorOps &ops, int lo, int himargin)
-    {
-        const Model &M = R.M;
-        const int e1 = d == 0 ? 1 : 0, e2 = d == 2 ? 1 : 2;
-        const int hi1 = M.G.dim[e1] - himargin, hi2 = M.G.dim[e2] - himargin;
-        if (hi1 <= lo || hi2 <= lo) return;
-        dim3 grid, blk;
-        face_dims(d, lo, hi1, hi2, grid, blk);
-        T *A = (T *)R.dev[field] + (long long)level * M.G.level;
-        face_mirror<T><<<grid, blk, 0, st>>>(A, M.G, ops, d, lo, hi1, hi2);
-        check();
-    }
-    template <typename T> void equation(const DevEq &eq, int lv0, int lv1, int d, int n, int lo, int himargin)
-    {
-        const Model &M = R.M;
-        const int e1 = d == 0 ? 1 : 0, e2 = d == 2 ? 1 : 2;
-        const int hi1 = M.G.dim[e1] - himargin, hi2 = M.G.dim[e2] - himargin;
-        if (hi1 <= lo || hi2 <= lo) return;
-        dim3 grid, blk;
-        face_dims(d, lo, hi1, hi2, grid, blk);
-        face_equation<T><<<grid, blk, 0, st>>>(ptrs(), M.G, eq, lv0, lv1, d, n, lo, hi1, hi2);
-        check();
-    }
-
     // ---- batched ghost loops: loops that cannot observe each other run in one launch
     template <typename T> void launch_batch(FaceBatch &B)
     {
@@ -335,13 +306,13 @@ struct Stepper {
         int total = 0;
         for (int k = 0; k < B.count; ++k) {
             const FaceLoop &L = B.loop[k];
-            const int w = L.d == 2 ? 8 : 128, h = 256 / w;
+            const int w = L.d == 2 ? 8 : 128, h = OPESCI_FACE_THREADS / w;
             B.nbx[k] = (L.hi2 - L.lo + w - 1) / w;
             B.start[k] = total;
             total += B.nbx[k] * ((L.hi1 - L.lo1 + h - 1) / h);
         }
         B.start[B.count] = total;
-        face_batch<T><<<total, 256, 0, st>>>(ptrs(), M.G, B);
+        face_batch<T><<<total, OPESCI_FACE_THREADS, 0, st>>>(ptrs(), M.G, B);
         check();
     }
     // loop ranges of one ghost loop: the reference uses [lo, dim - himargin) on both free axes
@@ -503,7 +474,7 @@ struct Stepper {
     }
 
     // fused stress+velocity launch (fused.cuh); only instantiated for so <= 4, fp32
-    template <int SO, typename T, int ARITH> void fused(int t0, int t1)
+    template <int SO, typename T, int ARITH> void fused(int t0, int t1, int mode = 0)
     {
         if constexpr (SO <= 4 && sizeof(T) == 4) {
             constexpr int M = SO / 2;
@@ -511,6 +482,8 @@ struct Stepper {
             const Model &Md = R.M;
             FusedArgs A;
             A.F = ptrs(); A.G = Md.G; A.C = Md.sc; A.t0 = t0; A.t1 = t1; A.xchunk = R.xchunk;
+            A.mode = mode;
+            for (int k = 0; k < 3; ++k) { A.box_lo[k] = R.box_lo[k]; A.box_hi[k] = R.box_hi[k]; }
             dim3 grid((Md.G.dim[2] - 2 * M + K::CZ - 1) / K::CZ, (Md.G.dim[1] - 2 * M + K::CY - 1) / K::CY, R.nchunks);
             fused_step<SO, ARITH><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
             check();
@@ -537,7 +510,7 @@ struct Stepper {
                     }
                     B.r[nb] = rg;
                     B.zwide[nb] = d == 2 ? 0 : 1;
-                    const int tw = d == 2 ? 4 : 64, th = 256 / tw;
+                    const int tw = d == 2 ? 4 : 64, th = OPESCI_FACE_THREADS / tw;
                     const int nz = rg.hi[2] - rg.lo[2], ny = rg.hi[1] - rg.lo[1], nx = rg.hi[0] - rg.lo[0];
                     B.nbz[nb] = nz > 0 ? (nz + tw - 1) / tw : 1;
                     B.nby[nb] = ny > 0 ? (ny + th - 1) / th : 1;
@@ -547,7 +520,7 @@ struct Stepper {
                 }
             B.start[6] = total;
             if (total == 0) return;
-            velocity_shell_kernel<SO, T, ARITH><<<total, 256, 0, st>>>(ptrs(), Md.G, Md.sc, t0, t1, B);
+            velocity_shell_kernel<SO, T, ARITH><<<total, OPESCI_FACE_THREADS, 0, st>>>(ptrs(), Md.G, Md.sc, t0, t1, B);
             check();
         }
     }
@@ -631,6 +604,38 @@ int setup_fused(Run &R)
         const double eff = waves / (double)((long long)(waves + 0.999999)) * len / (len + 2.0 * m + 2.0);
         if (eff > best) { best = eff; R.nchunks = nc; R.xchunk = len; }
     }
+    // (opt-in, OPESCI_OVERLAP: measured no gain on B200 -- a resident fused CTA pins the SM's L1/shared split at
+    // 228 KB shared, and the ghost kernels either cannot co-reside (default carve-out) or lose the L1 they live on)
+    // Overlap of the previous step's ghost loops with this step's fused kernel: tiles whose whole
+    // footprint (reads: core +- 2m in y,z and planes xa-2m .. xb+2m-1; writes: core) stays inside
+    // [2m+1, dim-2m-1)^3 touch no cell those loops read or write.  More x-chunks make more tiles
+    // independent (the two end chunks always depend on the x faces).
+    R.overlap = false;
+    if (M.slab.nranks == 1 && (p.flags & OPESCI_OVERLAP) && nx >= 6 * 48) {
+        const int nc = nx >= 8 * 96 ? 8 : 6;
+        R.nchunks = nc;
+        R.xchunk = (nx + nc - 1) / nc;
+        const int EY = 16, EZ = 64;
+        const int dims[3] = {M.G.dim[1], M.G.dim[2], M.G.dim[0]};
+        const int ntile[3] = {(p.dim[1] - 2 * m + CY - 1) / CY, (p.dim[2] - 2 * m + CZ - 1) / CZ, nc};
+        for (int a = 0; a < 3; ++a) {
+            int lo = ntile[a], hi = 0;
+            for (int k = 0; k < ntile[a]; ++k) {
+                int rlo, rhi;   // read footprint [rlo, rhi)
+                if (a == 0) { rlo = k * CY - m; rhi = k * CY + EY + m; }
+                else if (a == 1) { rlo = k * CZ - m; rhi = k * CZ + EZ + m; }
+                else {
+                    const int xa = m + k * R.xchunk;
+                    int xb = xa + R.xchunk;
+                    if (xb > dims[2] - m) xb = dims[2] - m;
+                    rlo = xa - 2 * m; rhi = xb + 2 * m + 1;
+                }
+                if (rlo >= 2 * m + 1 && rhi <= dims[a] - 2 * m - 1) { if (k < lo) lo = k; if (k + 1 > hi) hi = k + 1; }
+            }
+            R.box_lo[a] = lo; R.box_hi[a] = hi;
+        }
+        R.overlap = R.box_hi[0] > R.box_lo[0] && R.box_hi[1] > R.box_lo[1] && R.box_hi[2] > R.box_lo[2];
+    }
     R.fused = true;
     return 0;
 }
@@ -690,10 +695,80 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     CUDA_OK(cudaEventCreate(&e0));
     CUDA_OK(cudaEventCreate(&e1));
     const int nsteps = p.ntsteps;
-    const bool use_graph = !(p.flags & OPESCI_NO_CUDA_GRAPH) && nsteps >= 2 * period && !slabs;
+    int warm = p.warmup_steps > 0 ? p.warmup_steps : 0;   // the first `warmup_steps` steps run untimed (bench contract)
+    if (warm > nsteps) warm = nsteps;
     long long per_period = 0;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    const bool pipelined = staggered && R.fused && R.overlap && !slabs;
+    if (pipelined) {
+        // ---- software-pipelined stepping: the ghost loops + shell update of step n-1 (latency-bound, they
+        // leave most of the machine idle) run on a second stream concurrently with the tiles of step n that
+        // cannot see them; the remaining tiles of step n follow.  Same kernels, same per-cell order.
+        CUDA_OK(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        Stepper SB(R, st2);
+        auto ghost = [&](Stepper &X, int ti) {   // everything of step ti after the fused kernel
+            const int t0 = ti % 2, t1 = (t0 + 1) % 2;
+            X.template stress_bc<T>(t0, t1, false);
+            X.template velocity_shell<SO, T, ARITH>(t0, t1);
+            X.template velocity_bc<T>(t1);
+        };
+        auto step = [&](int ti, bool has_prev) -> int {
+            const int t0 = ti % 2, t1 = (t0 + 1) % 2;
+            if (has_prev) {
+                CUDA_OK(cudaEventRecord(ev_fork, st));
+                CUDA_OK(cudaStreamWaitEvent(st2, ev_fork, 0));
+                ghost(SB, ti - 1);
+                CUDA_OK(cudaEventRecord(ev_join, st2));
+            }
+            S.template fused<SO, T, ARITH>(t0, t1, 1);        // tiles independent of the ghost loops
+            if (has_prev) CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));
+            S.template fused<SO, T, ARITH>(t0, t1, 2);        // the remaining tiles
+            return 0;
+        };
+        const bool use_graph2 = !(p.flags & OPESCI_NO_CUDA_GRAPH) && nsteps >= 6;
+        if (use_graph2) {
+            // steady state of two consecutive steps (odd ti, then even ti), captured across both streams
+            CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const long long before = S.launches + SB.launches;
+            if (step(1, true) || step(2, true)) return 1;
+            per_period = S.launches + SB.launches - before;
+            CUDA_OK(cudaStreamEndCapture(st, &graph));
+            CUDA_OK(cudaGraphInstantiate(&gexec, graph, 0));
+            S.launches = SB.launches = 0;
+        }
+        long long graph_launches = 0;
+        auto run_range = [&](int a, int b) -> int {   // steps a .. b-1, pipeline drained at the end
+            int ti = a;
+            while (ti < b) {
+                if (gexec && ti > a && (ti & 1) && ti + 2 <= b) {
+                    CUDA_OK(cudaGraphLaunch(gexec, st));
+                    graph_launches += per_period;
+                    ti += 2;
+                } else {
+                    if (step(ti, ti > a)) return 1;
+                    ++ti;
+                }
+            }
+            if (b > a) ghost(S, b - 1);
+            return 0;
+        };
+        if (warm > 0 && run_range(0, warm)) return 1;
+        S.launches = SB.launches = 0;
+        graph_launches = 0;
+        CUDA_OK(cudaEventRecord(e0, st));
+        if (run_range(warm, nsteps)) return 1;
+        CUDA_OK(cudaEventRecord(e1, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        CUDA_OK(cudaStreamSynchronize(st2));
+        S.launches += SB.launches + graph_launches;
+        if (SB.err != cudaSuccess && S.err == cudaSuccess) S.err = SB.err;
+    } else {
+    const bool use_graph = !(p.flags & OPESCI_NO_CUDA_GRAPH) && nsteps >= 2 * period && !slabs;
     if (use_graph) {
         // one period of steps (time-level indices repeat with it) captured once, replayed
         CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -707,9 +782,6 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
         CUDA_OK(cudaGraphInstantiate(&gexec, graph, 0));
         S.launches = before;
     }
-    // the first `warmup_steps` steps run untimed (bench contract)
-    int warm = p.warmup_steps > 0 ? p.warmup_steps : 0;
-    if (warm > nsteps) warm = nsteps;
     int ti = 0;
     auto run_steps = [&](int upto) -> int {
         while (ti < upto) {
@@ -733,6 +805,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     CUDA_OK(cudaEventRecord(e0, st));
     if (run_steps(nsteps)) return 1;
     CUDA_OK(cudaEventRecord(e1, st));
+    }
     CUDA_OK(cudaStreamSynchronize(st));
     if (S.err != cudaSuccess) return fail("kernel launch failed in the time loop: %s", cudaGetErrorString(S.err));
     CUDA_OK(cudaGetLastError());
@@ -744,6 +817,9 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     if (graph) cudaGraphDestroy(graph);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (st2) cudaStreamDestroy(st2);
     return 0;
 }
 
