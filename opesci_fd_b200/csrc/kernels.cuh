@@ -236,6 +236,91 @@ acoustic_interior(FieldPtrs F, GridGeom G, AcousticCoefs C, int tprev, int tr, i
     u[(long long)tw * G.level + p] = acc;
 }
 
+
+// ---- regular-grid update, marching version (fp32, no derivative along z) -------------------------
+// The reference driver's PDE has x and y second derivatives only (tests/simplewaveequation.py:76,
+// SURVEY.md 0.7), so the contiguous axis carries no stencil: every thread owns four consecutive z
+// (one float4), marches along x with the 2M+1 planes of its own column in registers and reads the 2M
+// y-neighbours of the centre plane as float4 (L1 hits: they are the centre rows of neighbouring
+// threads).  12 B/point of compulsory traffic: read u[t1], read u[t0], write u[t2].
+template <int SO, int ARITH>
+__global__ void __launch_bounds__(256)
+acoustic_march(FieldPtrs F, GridGeom G, AcousticCoefs C, int tprev, int tr, int tw, int xchunk)
+{
+    constexpr int M = SO / 2;
+    const int z4 = 4 * (blockIdx.x * 32 + (threadIdx.x & 31));
+    const int y = M + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (z4 >= G.s[1] || y >= G.dim[1] - M) return;
+    const int xa = M + blockIdx.z * xchunk;
+    const int xb = min(xa + xchunk, G.dim[0] - M);
+    if (xa >= xb) return;
+    float *u = (float *)F.f[0];
+    const long long sx = G.s[0], sy = G.s[1];
+    const float *r1 = u + (long long)tr * G.level + (long long)y * sy + z4;
+    const float *r0 = u + (long long)tprev * G.level + (long long)y * sy + z4;
+    float *w2 = u + (long long)tw * G.level + (long long)y * sy + z4;
+    bool ok[4];
+    bool all = true;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) { ok[l] = z4 + l >= M && z4 + l < G.dim[2] - M; all = all && ok[l]; }
+    bool any = ok[0] || ok[1] || ok[2] || ok[3];
+    if (!any) return;
+    float4 win[2 * M + 1];   // planes x-M .. x+M of the own column
+#pragma unroll
+    for (int j = 0; j < 2 * M; ++j) win[j + 1] = *reinterpret_cast<const float4 *>(r1 + (long long)(xa - M + j) * sx);
+    for (int x = xa; x < xb; ++x) {
+#pragma unroll
+        for (int j = 0; j < 2 * M; ++j) win[j] = win[j + 1];
+        win[2 * M] = *reinterpret_cast<const float4 *>(r1 + (long long)(x + M) * sx);
+        const float4 prev = *reinterpret_cast<const float4 *>(r0 + (long long)x * sx);
+        float4 yn[2 * M];    // rows y+1..y+M, then y-1..y-M of the centre plane
+#pragma unroll
+        for (int o = 1; o <= M; ++o) {
+            yn[o - 1] = *reinterpret_cast<const float4 *>(r1 + (long long)x * sx + (long long)o * sy);
+            yn[M + o - 1] = *reinterpret_cast<const float4 *>(r1 + (long long)x * sx - (long long)o * sy);
+        }
+        float out[4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const float pv = (&prev.x)[l];
+            if (ARITH == OPESCI_ARITH_REFERENCE) {
+                float acc = -pv;
+                bool first = false;
+                if (C.present[0]) {
+#pragma unroll
+                    for (int o = 1; o <= M; ++o) term<float>(acc, first, C.c[0][o - 1], (&win[M + o].x)[l]);
+#pragma unroll
+                    for (int o = 1; o <= M; ++o) term<float>(acc, first, C.c[0][o - 1], (&win[M - o].x)[l]);
+                }
+                if (C.present[1]) {
+#pragma unroll
+                    for (int o = 1; o <= M; ++o) term<float>(acc, first, C.c[1][o - 1], (&yn[o - 1].x)[l]);
+#pragma unroll
+                    for (int o = 1; o <= M; ++o) term<float>(acc, first, C.c[1][o - 1], (&yn[M + o - 1].x)[l]);
+                }
+                term<float>(acc, first, C.centre, (&win[M].x)[l]);
+                out[l] = acc;
+            } else {
+                float sum = C.centre * (&win[M].x)[l];
+#pragma unroll
+                for (int o = 1; o <= M; ++o) {
+                    if (C.present[0]) sum += C.c[0][o - 1] * ((&win[M + o].x)[l] + (&win[M - o].x)[l]);
+                    if (C.present[1]) sum += C.c[1][o - 1] * ((&yn[o - 1].x)[l] + (&yn[M + o - 1].x)[l]);
+                }
+                out[l] = sum - pv;
+            }
+        }
+        float *dst = w2 + (long long)x * sx;
+        if (all) {
+            *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+        } else {
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+                if (ok[l]) dst[l] = out[l];
+        }
+    }
+}
+
 // ------------------------------------------------------------------ face (ghost-cell) kernels
 enum { TERM_MUL = 0, TERM_PLUS = 1, TERM_MINUS = 2 };
 struct DevTerm {

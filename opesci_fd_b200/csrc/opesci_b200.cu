@@ -289,12 +289,28 @@ struct Stepper {
     template <int SO, typename T, int ARITH> void acoustic(int tprev, int tr, int tw, bool init)
     {
         dim3 blk(64, 4);
-        if (init)
+        if (init) {
             acoustic_interior<SO, T, ARITH, false><<<interior_grid(blk), blk, 0, st>>>(
                 ptrs(), R.M.G, R.M.ac_init, tprev, tr, tw, (T)R.M.p.ac_init_const);
-        else
-            acoustic_interior<SO, T, ARITH, true><<<interior_grid(blk), blk, 0, st>>>(ptrs(), R.M.G, R.M.ac, tprev, tr,
-                                                                                       tw, (T)0);
+        } else {
+            bool marched = false;
+            if constexpr (sizeof(T) == 4) {
+                // no stencil along the contiguous axis (the reference driver's PDE): float4 marching kernel
+                if (!R.M.ac.present[2] && !(R.M.p.flags & OPESCI_FORCE_UNFUSED)) {
+                    const Model &Md = R.M;
+                    const int nx = Md.G.dim[0] - 2 * Md.m, ny = Md.G.dim[1] - 2 * Md.m;
+                    const int nbz = (int)((Md.G.s[1] / 4 + 31) / 32), nby = (ny + 7) / 8;
+                    int nchunks = (4 * 148 + nbz * nby - 1) / (nbz * nby);   // >= 4 blocks per SM in flight
+                    if (nchunks < 1) nchunks = 1;
+                    if (nchunks > nx / (4 * Md.m) && nx / (4 * Md.m) >= 1) nchunks = nx / (4 * Md.m);
+                    const int xchunk = (nx + nchunks - 1) / nchunks;
+                    acoustic_march<SO, ARITH><<<dim3(nbz, nby, (nx + xchunk - 1) / xchunk), 256, 0, st>>>(ptrs(), Md.G, Md.ac, tprev, tr, tw, xchunk);
+                    marched = true;
+                }
+            }
+            if (!marched)
+                acoustic_interior<SO, T, ARITH, true><<<interior_grid(blk), blk, 0, st>>>(ptrs(), R.M.G, R.M.ac, tprev, tr, tw, (T)0);
+        }
         check();
     }
 
