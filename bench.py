@@ -303,4 +303,13 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE line (the JSON record); everything else the run prints goes to stderr
+    _real_stdout = sys.stdout
+    sys.stdout = sys.stderr
+    _orig_print = print
+
+    def print(*a, **k):   # noqa: A001 -- the JSON line is the only print() in this file
+        k.setdefault("file", _real_stdout)
+        _orig_print(*a, **k)
+        _real_stdout.flush()
     sys.exit(main())
