@@ -75,7 +75,21 @@ enum {
     OPESCI_OP_MUL = 5,
     OPESCI_OP_NEG = 6,
     OPESCI_OP_DIV = 7,
-    OPESCI_OP_FIELD = 8  /* push (double)F[x][y][z]: only in `final_` programs */
+    OPESCI_OP_FIELD = 8, /* push (double)F[x][y][z]: only in `final_` programs */
+    /* heterogeneous (`read`) mode: the solution contains per-cell media, e.g.
+     * cos(...*sqrt(beta[_x][_y][_z]*mu[_x][_y][_z])) (opesci/staggeredgrid.py:648-653) */
+    OPESCI_OP_MEDIA = 9,   /* push (double)media[arg][x][y][z], arg = OPESCI_MEDIA_* */
+    OPESCI_OP_SQRT = 10,
+    OPESCI_OP_COS = 11,
+    OPESCI_OP_SIN = 12,
+    OPESCI_OP_ROUNDF = 13  /* round the top of the stack to float (a `float` typed C sub-expression) */
+};
+
+/* media arrays of the heterogeneous mode (opesci/staggeredgrid.py:262-276) */
+enum {
+    OPESCI_MEDIA_BETA = 0, OPESCI_MEDIA_LAMBDA, OPESCI_MEDIA_MU,
+    OPESCI_MEDIA_BETA1, OPESCI_MEDIA_BETA2, OPESCI_MEDIA_BETA3,
+    OPESCI_MEDIA_MU12, OPESCI_MEDIA_MU13, OPESCI_MEDIA_MU23, OPESCI_MEDIA_COUNT
 };
 
 typedef struct OpesciSolInstr {
@@ -153,6 +167,28 @@ typedef struct OpesciB200Params {
     float ac_init_centre;
     double ac_init_const;             /* the `1.0F*v*dt` term, evaluated in real_t by the host */
 
+    /* ---- staggered elastic, heterogeneous medium (`read` mode; staggeredgrid.py:249-276, 522-598) ----
+     * hetero != 0: the library derives beta, beta1-3, lambda, mu, mu12/13/23 from rho, vp, vs
+     * (with the ranges of the patched oracle: pointwise arrays on [0,dim), averaged ones
+     * on [0,dim-1)) and every emitted term becomes `literal*G[...]*media[x][y][z]` (a12).  fp32 only
+     * (the file reader is float*, src/opesciIO.cpp:319).  The c_* / lev_stress / lev_vnormal tables above
+     * are unused; lev_vtang (dx_d/dx_e) still applies. */
+    int32_t hetero;
+    int32_t media_plane0;            /* global index of the first x plane held by rho/vp/vs ... */
+    int32_t media_nplanes;           /* ... and how many planes they hold (whole array: 0, dim1) */
+    int32_t reserved_;
+    const float *rho, *vp, *vs;      /* HOST arrays [media_nplanes][dim2][dim3]: the flat float32 layout the
+                                      * reference's raw-binary reader expects: opesci/staggeredgrid.py:549-551 */
+    float h_c[3][OPESCI_MAX_M];      /* [axis d][k-1]: c_k*dt/dx_d */
+    float h_c2[3][OPESCI_MAX_M];     /* 2*c_k*dt/dx_d: the `*mu` terms of the own-axis window of T_dd */
+    /* Levander with per-cell media (so == 4), P_d = product of the two spacings other than dx_d: */
+    float h_lev_den[3][2];           /* [face d]: denominator D = a*lambda + b*mu, a = 12 P_d, b = 24 P_d */
+    float h_lev_own[3][3][2];        /* [face d][axis f][k-1] = 48 P_d c_k dt/dx_f: window of V_f in T_ff, as
+                                      * `*lambda*mu/D` and `*pow(mu,2)/D` terms */
+    float h_lev_oth[3][3][2];        /* [face d][axis f][k-1] = 24 P_d c_k dt/dx_f: window of V_f in T_ee, e != f,
+                                      * as `*lambda*mu/D` terms */
+    float h_vn[3][2];                /* velocity normal ghost, [axis g]: P_g and 2 P_g */
+
     OpesciFieldSpec fields[OPESCI_MAX_FIELDS];
 } OpesciB200Params;
 
@@ -199,6 +235,9 @@ int opesci_b200_release_host(void);
 int opesci_b200_comm_unique_id(void *out_id, int nbytes);
 int opesci_b200_comm_init(int rank, int nranks, const void *id, int nbytes);
 int opesci_b200_comm_finalize(void);
+/* the planes [L0,L1) of global dim1 that rank `rank` of `nranks` stores (its slab plus halos): what a
+ * heterogeneous run has to supply in rho/vp/vs (media_plane0 = L0, media_nplanes = L1-L0) */
+int opesci_b200_slab_range(int rank, int nranks, int gdim1, int so, int *L0, int *L1);
 /* 1 if this library was built with the CUDA kernels (0 for the CPU oracle build) */
 int opesci_b200_is_cuda(void);
 

@@ -16,6 +16,8 @@ OPESCI_MAX_TABLES = 12
 OPESCI_MAX_PROG = 48
 
 OP_TABLE, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_DIV, OP_FIELD = 1, 2, 3, 4, 5, 6, 7, 8
+OP_MEDIA, OP_SQRT, OP_COS, OP_SIN, OP_ROUNDF = 9, 10, 11, 12, 13
+MEDIA_NAMES = ['beta', 'lambda', 'mu', 'beta1', 'beta2', 'beta3', 'mu12', 'mu13', 'mu23']
 
 KIND_STAGGERED_ELASTIC = 1
 KIND_REGULAR_ACOUSTIC = 2
@@ -78,6 +80,14 @@ class OpesciB200Params(Structure):
         ("ac_init_coef", (c_float * OPESCI_MAX_M) * 3),
         ("ac_init_centre", c_float),
         ("ac_init_const", c_double),
+        ("hetero", c_int32), ("media_plane0", c_int32), ("media_nplanes", c_int32), ("reserved_", c_int32),
+        ("rho", POINTER(c_float)), ("vp", POINTER(c_float)), ("vs", POINTER(c_float)),
+        ("h_c", (c_float * OPESCI_MAX_M) * 3),
+        ("h_c2", (c_float * OPESCI_MAX_M) * 3),
+        ("h_lev_den", (c_float * 2) * 3),
+        ("h_lev_own", ((c_float * 2) * 3) * 3),
+        ("h_lev_oth", ((c_float * 2) * 3) * 3),
+        ("h_vn", (c_float * 2) * 3),
         ("fields", OpesciFieldSpec * OPESCI_MAX_FIELDS),
     ]
 
@@ -87,7 +97,7 @@ EXPORTED_SYMBOLS = [
     "opesci_b200_last_error", "opesci_b200_convergence_f64", "opesci_b200_last_timing",
     "opesci_b200_is_cuda", "opesci_b200_time_kernels",
     "opesci_b200_comm_unique_id", "opesci_b200_comm_init", "opesci_b200_comm_finalize",
-    "opesci_b200_reserve_host", "opesci_b200_release_host",
+    "opesci_b200_reserve_host", "opesci_b200_release_host", "opesci_b200_slab_range",
 ]
 SLAB_HALO = 8
 COMM_ID_BYTES = 128
@@ -127,6 +137,10 @@ def bind(lib):
         lib.opesci_b200_comm_init.restype = ctypes.c_int
         lib.opesci_b200_comm_finalize.argtypes = []
         lib.opesci_b200_comm_finalize.restype = ctypes.c_int
+    if hasattr(lib, "opesci_b200_slab_range"):
+        lib.opesci_b200_slab_range.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               POINTER(ctypes.c_int), POINTER(ctypes.c_int)]
+        lib.opesci_b200_slab_range.restype = ctypes.c_int
     lib.opesci_b200_is_cuda.argtypes = []
     lib.opesci_b200_is_cuda.restype = ctypes.c_int
     return lib

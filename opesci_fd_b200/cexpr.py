@@ -13,6 +13,12 @@ without generating code, this module
      the reference binary links) for function calls -- into a constant or a 1-D table, and
   4. emits the remaining multi-coordinate `+ - * /` tree as a postfix program that the
      device executes in IEEE double (include/opesci_b200.h: OpesciSolProgram).
+
+Heterogeneous (`read`) mode: the printed solution contains per-cell media accesses such as
+`sqrt(beta[_x][_y][_z]*mu[_x][_y][_z])` (reference: opesci/staggeredgrid.py:648-653).  They become
+OP_MEDIA operands; `float`-typed per-cell arithmetic is the double operation followed by OP_ROUNDF
+(double rounding is innocuous for + - * / sqrt from 24 to 53 bits), and sqrt / cos / sin of a per-cell
+argument run on the device.
 """
 import math
 import re
@@ -156,6 +162,17 @@ class Variables(object):
     def field(self, name, ctype):
         self.table[name] = (ctype, frozenset(["F"]), None)
 
+    def media(self, name, ctype, media_id):
+        """per-cell array operand `name` (text `name[_x][_y][_z]` is rewritten to `name__cell`)"""
+        self.table[name + "__cell"] = (ctype, frozenset(["C%d" % media_id]), None)
+
+
+def _per_cell(deps):
+    return any(isinstance(d, str) for d in deps)
+
+
+_DEVICE_CALLS = {"sqrt": abi.OP_SQRT, "cos": abi.OP_COS, "sin": abi.OP_SIN}
+
 
 def _cast(data, ctype):
     return None if data is None else np.asarray(data).astype(_NP[ctype])[()]
@@ -182,7 +199,7 @@ def _annotate(n, variables):
         a, b = n.args
         n.ctype = max(a.ctype, b.ctype)   # usual arithmetic conversions: int < float < double
         n.deps = a.deps | b.deps
-        if len(n.deps) <= 1 and "F" not in n.deps:
+        if len(n.deps) <= 1 and not _per_cell(n.deps):
             x, y = _cast(a.data, n.ctype), _cast(b.data, n.ctype)
             with np.errstate(all="ignore"):
                 if n.name == "+":
@@ -201,6 +218,8 @@ def _annotate(n, variables):
             raise NotImplementedError("function %r in a solution expression" % n.name)
         n.ctype = DOUBLE   # ::sin(double) etc.: <cmath> puts only the double versions in ::
         n.deps = frozenset().union(*[a.deps for a in n.args])
+        if _per_cell(n.deps) and "F" not in n.deps and n.name in _DEVICE_CALLS and len(n.args) == 1:
+            return   # evaluated per cell on the device
         if len(n.deps) > 1 or "F" in n.deps:
             raise NotImplementedError("%s() of more than one coordinate: not separable" % n.name)
         fn = _FUNCS[n.name]
@@ -224,10 +243,13 @@ class ProgramBuilder(object):
         if "F" in n.deps and n.kind == "var":
             self.instr.append((abi.OP_FIELD, 0, 0.0))
             return
+        if n.kind == "var" and _per_cell(n.deps):
+            self.instr.append((abi.OP_MEDIA, int(next(iter(n.deps))[1:]), 0.0))
+            return
         if len(n.deps) == 0:
             self.instr.append((abi.OP_CONST, 0, float(np.float64(n.data))))
             return
-        if len(n.deps) == 1 and "F" not in n.deps:
+        if len(n.deps) == 1 and not _per_cell(n.deps):
             axis = next(iter(n.deps))
             tab = np.ascontiguousarray(np.broadcast_to(np.asarray(n.data, dtype=np.float64),
                                                        (self.dims[axis],)), dtype=np.float64)
@@ -243,12 +265,17 @@ class ProgramBuilder(object):
             self.emit(n.args[0])
             self.instr.append((abi.OP_NEG, 0, 0.0))
         elif n.kind == "bin":
-            if n.ctype != DOUBLE:
-                raise NotImplementedError("multi-coordinate %s in single precision" % n.name)
+            if n.ctype == INT:
+                raise NotImplementedError("multi-coordinate integer %s" % n.name)
             self.emit(n.args[0])
             self.emit(n.args[1])
             self.instr.append(({"+": abi.OP_ADD, "-": abi.OP_SUB, "*": abi.OP_MUL,
                                 "/": abi.OP_DIV}[n.name], 0, 0.0))
+            if n.ctype == FLOAT:
+                self.instr.append((abi.OP_ROUNDF, 0, 0.0))
+        elif n.kind == "call" and n.name in _DEVICE_CALLS:
+            self.emit(n.args[0])
+            self.instr.append((_DEVICE_CALLS[n.name], 0, 0.0))
         else:
             raise NotImplementedError("cannot lower node %r" % n.kind)
 
@@ -270,10 +297,19 @@ class Program(object):
         for k, (op, arg, val) in enumerate(self.instr):
             cprog.instr[k].op, cprog.instr[k].arg, cprog.instr[k].value = op, arg, val
 
-    def evaluate(self, x, y, z, fieldval=0.0):
+    def evaluate(self, x, y, z, fieldval=0.0, media=None):
         """Pure-python execution of the program at one cell (tests only)."""
         st, idx = [], (x, y, z)
         for op, arg, val in self.instr:
+            if op == abi.OP_MEDIA:
+                st.append(np.float64(media[arg][x, y, z]))
+                continue
+            if op in (abi.OP_SQRT, abi.OP_COS, abi.OP_SIN):
+                st[-1] = np.float64({abi.OP_SQRT: math.sqrt, abi.OP_COS: math.cos, abi.OP_SIN: math.sin}[op](float(st[-1])))
+                continue
+            if op == abi.OP_ROUNDF:
+                st[-1] = np.float64(np.float32(st[-1]))
+                continue
             if op == abi.OP_TABLE:
                 st.append(np.float64(self.tables[arg][1][idx[self.tables[arg][0]]]))
             elif op == abi.OP_CONST:
@@ -292,6 +328,7 @@ class Program(object):
 
 def compile_expression(text, variables, dims):
     """C expression text -> Program (see module docstring)."""
+    text = re.sub(r"\b([A-Za-z_][A-Za-z_0-9]*)\[_x\]\[_y\]\[_z\]", r"\1__cell", text)
     tree = Parser(text).parse()
     _annotate(tree, variables)
     pb = ProgramBuilder(dims)

@@ -26,6 +26,10 @@ enum { F_U = 0, F_V, F_W, F_TXX, F_TYY, F_TZZ, F_TXY, F_TYZ, F_TXZ };
 struct FieldPtrs {
     void *f[OPESCI_MAX_FIELDS];   // base of [nlevels][dim1][dim2][dim3]
 };
+// heterogeneous mode: the nine derived media arrays (OPESCI_MEDIA_*), same pitched layout as one time level
+struct MediaPtrs {
+    const float *m[OPESCI_MEDIA_COUNT];
+};
 
 struct GridGeom {
     int dim[3];
@@ -323,14 +327,23 @@ acoustic_march(FieldPtrs F, GridGeom G, AcousticCoefs C, int tprev, int tr, int 
 
 // ------------------------------------------------------------------ face (ghost-cell) kernels
 enum { TERM_MUL = 0, TERM_PLUS = 1, TERM_MINUS = 2 };
+// media factors of one emitted term in heterogeneous mode, applied left to right after v = coef*G
+// (the printed C of the patched reference, oracle/opesci_oracle.c):
+//   MK_A v*A   MK_A_DIV v*A/D   MK_AB_DIV v*A*B/D   MK_SQ_DIV v*pow(B,2)/D (double)   MK_RATIO v*A/B
+// with D = da*lambda + db*mu of the equation.
+enum { MK_NONE = 0, MK_A, MK_A_DIV, MK_AB_DIV, MK_SQ_DIV, MK_RATIO };
 struct DevTerm {
     int kind, field, level;
     float coef;
     long long off;
+    int mk, ma, mb, pad;
+    long long moffa, moffb;
 };
-#define OPESCI_MAX_FACE_TERMS 12
+#define OPESCI_MAX_FACE_TERMS 16
 struct DevEq {
     int out, out_level, nterm, pad;
+    float da, db;
+    long long doff;
     DevTerm term[OPESCI_MAX_FACE_TERMS];
 };
 
@@ -366,7 +379,7 @@ struct FaceBatch {
 #define OPESCI_FACE_THREADS 128
 template <typename T>
 __global__ void __launch_bounds__(OPESCI_FACE_THREADS)
-face_batch(FieldPtrs F, GridGeom G, const __grid_constant__ FaceBatch B)
+face_batch(FieldPtrs F, GridGeom G, const __grid_constant__ FaceBatch B, MediaPtrs MD)
 {
     int li = 0;
     for (int k = 1; k < B.count; ++k)
@@ -392,18 +405,39 @@ face_batch(FieldPtrs F, GridGeom G, const __grid_constant__ FaceBatch B)
         const long long p = q + (long long)L.n * G.s[d];
         const long long lv[2] = {(long long)L.lv0 * G.level, (long long)L.lv1 * G.level};
         T acc = 0;
-        bool first = true;
+        double accd = 0.0;   // the running sum once a double-typed term (pow(mu,2)) has been met
+        bool first = true, wide = false;
         for (int k = 0; k < L.eq.nterm; ++k) {
             const DevTerm &t = L.eq.term[k];
             const T g = ((const T *)F.f[t.field])[lv[t.level] + p + t.off];
-            T v;
-            if (t.kind == TERM_MUL) v = mul_rn<T>((T)t.coef, g);
-            else if (t.kind == TERM_PLUS) v = g;
-            else v = -g;
-            acc = first ? v : add_rn<T>(acc, v);
+            T v = t.kind == TERM_MUL ? mul_rn<T>((T)t.coef, g) : g;
+            if (t.mk != MK_NONE) {
+                // heterogeneous Levander terms: fp32 only, the reference's left-to-right evaluation
+                const float D = __fadd_rn(__fmul_rn(L.eq.da, MD.m[OPESCI_MEDIA_LAMBDA][p + L.eq.doff]),
+                                          __fmul_rn(L.eq.db, MD.m[OPESCI_MEDIA_MU][p + L.eq.doff]));
+                const float A = MD.m[t.ma][p + t.moffa], Bm = MD.m[t.mb][p + t.moffb];
+                if (t.mk == MK_SQ_DIV) {
+                    double vd = __ddiv_rn(__dmul_rn((double)v, __dmul_rn((double)Bm, (double)Bm)), (double)D);
+                    if (t.kind == TERM_MINUS) vd = -vd;
+                    accd = first ? vd : __dadd_rn(wide ? accd : (double)acc, vd);
+                    first = false;
+                    wide = true;
+                    continue;
+                }
+                float w = (float)v;
+                if (t.mk == MK_A) w = __fmul_rn(w, A);
+                else if (t.mk == MK_A_DIV) w = __fdiv_rn(__fmul_rn(w, A), D);
+                else if (t.mk == MK_AB_DIV) w = __fdiv_rn(__fmul_rn(__fmul_rn(w, A), Bm), D);
+                else w = __fdiv_rn(__fmul_rn(w, A), Bm);
+                v = (T)w;
+            }
+            if (t.kind == TERM_MINUS) v = -v;
+            if (first) acc = v;
+            else if (wide) accd = __dadd_rn(accd, (double)v);
+            else acc = add_rn<T>(acc, v);
             first = false;
         }
-        ((T *)F.f[L.eq.out])[lv[L.eq.out_level] + p] = acc;
+        ((T *)F.f[L.eq.out])[lv[L.eq.out_level] + p] = wide ? (T)accd : acc;
     }
 }
 
@@ -412,10 +446,11 @@ struct DevProgram {
     int n_instr, n_tables;
     int table_axis[OPESCI_MAX_TABLES];
     const double *table[OPESCI_MAX_TABLES];   // device pointers
+    const float *media[OPESCI_MEDIA_COUNT];   // heterogeneous mode (OPESCI_OP_MEDIA), else null
     OpesciSolInstr instr[OPESCI_MAX_PROG];
 };
 
-__device__ __forceinline__ double run_program(const DevProgram &pr, int x, int y, int z, double fieldval)
+__device__ __forceinline__ double run_program(const DevProgram &pr, int x, int y, int z, double fieldval, long long cell)
 {
     double st[OPESCI_PROG_STACK];
     int sp = 0;
@@ -431,6 +466,16 @@ __device__ __forceinline__ double run_program(const DevProgram &pr, int x, int y
             st[sp++] = fieldval;
         } else if (op == OPESCI_OP_NEG) {
             st[sp - 1] = -st[sp - 1];
+        } else if (op == OPESCI_OP_MEDIA) {
+            st[sp++] = (double)pr.media[pr.instr[i].arg][cell];
+        } else if (op == OPESCI_OP_SQRT) {
+            st[sp - 1] = __dsqrt_rn(st[sp - 1]);
+        } else if (op == OPESCI_OP_COS) {
+            st[sp - 1] = cos(st[sp - 1]);
+        } else if (op == OPESCI_OP_SIN) {
+            st[sp - 1] = sin(st[sp - 1]);
+        } else if (op == OPESCI_OP_ROUNDF) {
+            st[sp - 1] = (double)(float)st[sp - 1];
         } else {
             --sp;
             const double a = st[sp - 1], b = st[sp];
@@ -455,7 +500,8 @@ __global__ void init_field(T *__restrict__ A /* level 0 */, GridGeom G, Range3 R
     const int y = R.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
     const int x = R.lo[0] + blockIdx.z;
     if (z >= R.hi[2] || y >= R.hi[1]) return;
-    A[(long long)x * G.s[0] + (long long)y * G.s[1] + z] = (T)run_program(pr, x, y, z, 0.0);
+    const long long cell = (long long)x * G.s[0] + (long long)y * G.s[1] + z;
+    A[cell] = (T)run_program(pr, x, y, z, 0.0, cell);
 }
 
 // per-block partial sums of residual^2 in double; partial[blockIdx linear]
@@ -474,7 +520,8 @@ __global__ void l2_partial(const T *__restrict__ A /* level ti */, GridGeom G, R
     const int x = R.lo[0] + blockIdx.z;
     double v = 0.0;
     if (z < R.hi[2] && y < R.hi[1]) {
-        const double e = run_program(pr, x, y, z, (double)A[(long long)x * G.s[0] + (long long)y * G.s[1] + z]);
+        const long long cell = (long long)x * G.s[0] + (long long)y * G.s[1] + z;
+        const double e = run_program(pr, x, y, z, (double)A[cell], cell);
         v = e * e;
     }
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);

@@ -24,6 +24,7 @@
 
 #include "../../include/opesci_slab.h"
 #include "fused.cuh"
+#include "hetero.cuh"
 #include "kernels.cuh"
 
 using namespace opesci;
@@ -105,6 +106,7 @@ struct Model {
     int m = 0;
     GridGeom G;
     StaggeredCoefs sc;
+    HeteroCoefs hc;                               // heterogeneous (`read`) mode
     AcousticCoefs ac, ac_init;
     DevEq lev_stress_eq[3][3];
     DevEq lev_vel_eq[3][3][2];
@@ -119,6 +121,7 @@ struct Run {
     Model M;
     void *dev[OPESCI_MAX_FIELDS] = {};
     void *host[OPESCI_MAX_FIELDS] = {};
+    float *media[OPESCI_MEDIA_COUNT] = {};   // heterogeneous mode: derived media arrays (one level each)
     bool host_pinned = false;
     double *d_tables = nullptr;
     DevProgram *d_prog = nullptr;   // [nfields][2]
@@ -173,6 +176,14 @@ void push(DevEq &eq, int kind, int field, int level, long long off, float coef)
 {
     DevTerm &t = eq.term[eq.nterm++];
     t.kind = kind; t.field = field; t.level = level; t.off = off; t.coef = coef;
+    t.mk = MK_NONE; t.ma = t.mb = 0; t.pad = 0; t.moffa = t.moffb = 0;
+}
+void push_m(DevEq &eq, int kind, int field, int level, long long off, float coef, int mk, int ma, long long moffa, int mb,
+            long long moffb)
+{
+    push(eq, kind, field, level, off, coef);
+    DevTerm &t = eq.term[eq.nterm - 1];
+    t.mk = mk; t.ma = ma; t.mb = mb; t.moffa = moffa; t.moffb = moffb;
 }
 const int NORMAL_OF_AXIS[3] = {F_TXX, F_TYY, F_TZZ};
 const int VEL_OF_AXIS[3] = {F_U, F_V, F_W};
@@ -247,6 +258,98 @@ void build_levander(Model &M)
             }
 }
 
+// Levander free-surface loops with per-cell media (so == 4): the emitted forms of the patched reference,
+// term for term (oracle/opesci_oracle.c:build_levander_hetero documents them; parity is bit-exact through
+// the oracle, tests/test_oracle_golden.py + tests/test_gpu_parity.py).
+int mu_of_pair(int a, int b)
+{
+    if (a > b) { int t = a; a = b; b = t; }
+    if (a == 0 && b == 1) return OPESCI_MEDIA_MU12;
+    if (a == 1 && b == 2) return OPESCI_MEDIA_MU23;
+    return OPESCI_MEDIA_MU13;
+}
+// backward window, m == 2, printer order +1, -1, -2, 0; `nv` media variants per offset
+void push_window_bwd2_m(DevEq &eq, int field, long long stride, const float *c, int nv, const int *mk, const int *ma, const int *mb)
+{
+    const long long off[4] = {stride, -stride, -2 * stride, 0};
+    const float coef[4] = {c[1], -c[0], -c[1], c[0]};
+    for (int o = 0; o < 4; ++o)
+        for (int j = 0; j < nv; ++j) push_m(eq, TERM_MUL, field, 0, off[o], coef[o], mk[j], ma[j], 0, mb[j], 0);
+}
+void build_levander_hetero(Model &M)
+{
+    const OpesciB200Params &p = M.p;
+    const long long *s = M.G.s;
+    const int LAM = OPESCI_MEDIA_LAMBDA, MU = OPESCI_MEDIA_MU;
+    for (int d = 0; d < 3; ++d)
+        for (int e = 0; e < 3; ++e) {
+            DevEq &eq = M.lev_stress_eq[d][e];
+            eq.out = NORMAL_OF_AXIS[e]; eq.out_level = 1; eq.nterm = 0;
+            if (e == d) continue;
+            eq.da = p.h_lev_den[d][0]; eq.db = p.h_lev_den[d][1]; eq.doff = 0;
+            push_m(eq, TERM_MUL, eq.out, 0, 0, eq.da, MK_A_DIV, LAM, 0, 0, 0);
+            push_m(eq, TERM_MUL, eq.out, 0, 0, eq.db, MK_A_DIV, MU, 0, 0, 0);
+            for (int f = 0; f < 3; ++f) {
+                if (f == d) continue;
+                if (f == e) {
+                    const int mk[2] = {MK_AB_DIV, MK_SQ_DIV}, ma[2] = {LAM, 0}, mb[2] = {MU, MU};
+                    push_window_bwd2_m(eq, VEL_OF_AXIS[f], s[f], p.h_lev_own[d][f], 2, mk, ma, mb);
+                } else {
+                    const int mk[1] = {MK_AB_DIV}, ma[1] = {LAM}, mb[1] = {MU};
+                    push_window_bwd2_m(eq, VEL_OF_AXIS[f], s[f], p.h_lev_oth[d][f], 1, mk, ma, mb);
+                }
+            }
+        }
+    for (int d = 0; d < 3; ++d)
+        for (int a = 0; a < 3; ++a)
+            for (int side = 0; side < 2; ++side) {
+                DevEq &eq = M.lev_vel_eq[d][a][side];
+                const long long sd = s[d];
+                const float sgn = side == 0 ? 1.0f : -1.0f;
+                eq.out = VEL_OF_AXIS[a]; eq.out_level = 0; eq.nterm = 0;
+                if (a == d) {
+                    const long long plane = side == 0 ? sd : 0, selfoff = side == 0 ? sd : -sd;
+                    eq.da = p.h_vn[d][0]; eq.db = p.h_vn[d][1]; eq.doff = plane;
+                    for (int g = 0; g < 3; ++g) {
+                        if (g == d) {
+                            push_m(eq, TERM_MUL, VEL_OF_AXIS[d], 0, selfoff, eq.da, MK_A_DIV, LAM, plane, 0, 0);
+                            push_m(eq, TERM_MUL, VEL_OF_AXIS[d], 0, selfoff, eq.db, MK_A_DIV, MU, plane, 0, 0);
+                        } else {
+                            const float c = p.h_vn[g][0];
+                            push_m(eq, TERM_MUL, VEL_OF_AXIS[g], 0, plane - s[g], -sgn * c, MK_A_DIV, LAM, plane, 0, 0);
+                            push_m(eq, TERM_MUL, VEL_OF_AXIS[g], 0, plane, sgn * c, MK_A_DIV, LAM, plane, 0, 0);
+                        }
+                    }
+                } else {
+                    const int e = a;
+                    const float g = p.lev_vtang[d][e];
+                    const long long se = s[e];
+                    const long long pl0 = side == 0 ? 0 : -sd, pl1 = side == 0 ? sd : -2 * sd;
+                    const long long sf0 = side == 0 ? sd : -sd, sf1 = side == 0 ? 2 * sd : -2 * sd;
+                    const int mu = mu_of_pair(d, e);
+#define OPESCI_RATIO MK_RATIO, mu, pl1, mu, pl0
+                    if (d < e) {
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl0 + se, sgn * g);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl0, -sgn * g);
+                        push_m(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl1 + se, -sgn * g, OPESCI_RATIO);
+                        push_m(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl1, sgn * g, OPESCI_RATIO);
+                        push(eq, TERM_PLUS, VEL_OF_AXIS[e], 0, sf0, 1.0f);
+                        push_m(eq, TERM_PLUS, VEL_OF_AXIS[e], 0, sf0, 1.0f, OPESCI_RATIO);
+                        push_m(eq, TERM_MINUS, VEL_OF_AXIS[e], 0, sf1, 1.0f, OPESCI_RATIO);
+                    } else {
+                        push(eq, TERM_PLUS, VEL_OF_AXIS[e], 0, sf0, 1.0f);
+                        push_m(eq, TERM_PLUS, VEL_OF_AXIS[e], 0, sf0, 1.0f, OPESCI_RATIO);
+                        push_m(eq, TERM_MINUS, VEL_OF_AXIS[e], 0, sf1, 1.0f, OPESCI_RATIO);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, se + pl0, sgn * g);
+                        push_m(eq, TERM_MUL, VEL_OF_AXIS[d], 0, se + pl1, -sgn * g, OPESCI_RATIO);
+                        push(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl0, -sgn * g);
+                        push_m(eq, TERM_MUL, VEL_OF_AXIS[d], 0, pl1, sgn * g, OPESCI_RATIO);
+                    }
+#undef OPESCI_RATIO
+                }
+            }
+}
+
 // ------------------------------------------------------------------ launch helpers
 struct Stepper {
     const Run &R;
@@ -260,6 +363,12 @@ struct Stepper {
         FieldPtrs F;
         for (int f = 0; f < OPESCI_MAX_FIELDS; ++f) F.f[f] = R.dev[f];
         return F;
+    }
+    MediaPtrs media() const
+    {
+        MediaPtrs MD;
+        for (int k = 0; k < OPESCI_MEDIA_COUNT; ++k) MD.m[k] = R.media[k];
+        return MD;
     }
     void check()
     {
@@ -277,12 +386,26 @@ struct Stepper {
     template <int SO, typename T, int ARITH> void stress(int t0, int t1)
     {
         dim3 blk(64, 4);
+        if constexpr (sizeof(T) == 4) {
+            if (R.M.p.hetero) {
+                stress_interior_h<SO, ARITH><<<interior_grid(blk), blk, 0, st>>>(ptrs(), media(), R.M.G, R.M.hc, t0, t1);
+                check();
+                return;
+            }
+        }
         stress_interior<SO, T, ARITH><<<interior_grid(blk), blk, 0, st>>>(ptrs(), R.M.G, R.M.sc, t0, t1);
         check();
     }
     template <int SO, typename T, int ARITH> void velocity(int t0, int t1)
     {
         dim3 blk(64, 4);
+        if constexpr (sizeof(T) == 4) {
+            if (R.M.p.hetero) {
+                velocity_interior_h<SO, ARITH><<<interior_grid(blk), blk, 0, st>>>(ptrs(), media(), R.M.G, R.M.hc, t0, t1);
+                check();
+                return;
+            }
+        }
         velocity_interior<SO, T, ARITH><<<interior_grid(blk), blk, 0, st>>>(ptrs(), R.M.G, R.M.sc, t0, t1);
         check();
     }
@@ -328,7 +451,7 @@ struct Stepper {
             total += B.nbx[k] * ((L.hi1 - L.lo1 + h - 1) / h);
         }
         B.start[B.count] = total;
-        face_batch<T><<<total, OPESCI_FACE_THREADS, 0, st>>>(ptrs(), M.G, B);
+        face_batch<T><<<total, OPESCI_FACE_THREADS, 0, st>>>(ptrs(), M.G, B, media());
         check();
     }
     // loop ranges of one ghost loop: the reference uses [lo, dim - himargin) on both free axes
@@ -581,6 +704,7 @@ int setup_fused(Run &R)
     const OpesciB200Params &p = M.p;
     R.fused = false;
     if (p.kind != OPESCI_KIND_STAGGERED_ELASTIC || p.is_double || p.so > 4 || (p.flags & OPESCI_FORCE_UNFUSED)) return 0;
+    if (p.hetero) return 0;   // heterogeneous media: two-pass kernels (hetero.cuh)
     for (int d = 0; d < 3; ++d)
         if (M.G.dim[d] < 6 * M.m + 4) return 0;   // no deep interior worth fusing
     static EncodeTiledFn encode = nullptr;
@@ -916,6 +1040,8 @@ void release(Run *R)
         if (R->dev[f]) cudaFree(R->dev[f]);
         if (R->host[f]) pool_release(R->host[f]);
     }
+    for (int k = 0; k < OPESCI_MEDIA_COUNT; ++k)
+        if (R->media[k]) cudaFree(R->media[k]);
     if (R->d_tables) cudaFree(R->d_tables);
     if (R->d_prog) cudaFree(R->d_prog);
     delete R;
@@ -940,10 +1066,58 @@ int upload_programs(Run &R)
                 dst.table_axis[t] = src.table_axis[t];
                 dst.table[t] = R.d_tables + M.table_off[f][w][t] + (src.table_axis[t] == 0 ? M.slab.L0 : 0);
             }
-            for (int i = 0; i < src.n_instr; ++i) dst.instr[i] = src.instr[i];
+            for (int i = 0; i < src.n_instr; ++i) {
+                dst.instr[i] = src.instr[i];
+                if (src.instr[i].op == OPESCI_OP_MEDIA && (!M.p.hetero || !R.media[0]))
+                    return fail("solution program reads media arrays: needs a heterogeneous grid produced by opesci_execute");
+            }
+            for (int k = 0; k < OPESCI_MEDIA_COUNT; ++k) dst.media[k] = R.media[k];
         }
     CUDA_OK(cudaMalloc(&R.d_prog, progs.size() * sizeof(DevProgram)));
     CUDA_OK(cudaMemcpy(R.d_prog, progs.data(), progs.size() * sizeof(DevProgram), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// a11 (opesci/staggeredgrid.py:522-598): upload this rank's planes of rho, vp, vs and derive the nine
+// media arrays on the device.  Arrays are zero-filled first: like the reference's, cells outside the loop
+// ranges stay 0.
+int setup_media(Run &R, cudaStream_t st)
+{
+    const Model &M = R.M;
+    const OpesciB200Params &p = M.p;
+    if (!p.hetero) return 0;
+    if (!p.rho || !p.vp || !p.vs) return fail("heterogeneous media: rho/vp/vs missing");
+    if (p.media_plane0 > M.slab.L0 || p.media_plane0 + p.media_nplanes < M.slab.L1)
+        return fail("heterogeneous media: rho/vp/vs do not cover the planes this rank stores (opesci_b200_slab_range)");
+    const size_t bytes = (size_t)M.G.level * sizeof(float);
+    float *in[3] = {nullptr, nullptr, nullptr};
+    const float *src[3] = {p.rho, p.vp, p.vs};
+    const size_t host_row = (size_t)p.dim[2] * sizeof(float), dev_row = (size_t)M.G.s[1] * sizeof(float);
+    const size_t rows = (size_t)M.G.dim[0] * p.dim[1];
+    const size_t shift = (size_t)(M.slab.L0 - p.media_plane0) * p.dim[1] * p.dim[2];
+    auto cleanup = [&]() { for (float *q : in) if (q) cudaFree(q); };
+    for (int k = 0; k < 3; ++k) {
+        if (cudaMalloc(&in[k], bytes) != cudaSuccess || cudaMemsetAsync(in[k], 0, bytes, st) != cudaSuccess ||
+            cudaMemcpy2DAsync(in[k], dev_row, src[k] + shift, host_row, host_row, rows, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            cleanup();
+            return fail("heterogeneous media: upload failed (%s)", cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    MediaOut O;
+    for (int k = 0; k < OPESCI_MEDIA_COUNT; ++k) {
+        if (cudaMalloc(&R.media[k], bytes) != cudaSuccess || cudaMemsetAsync(R.media[k], 0, bytes, st) != cudaSuccess) {
+            cleanup();
+            return fail("heterogeneous media: cudaMalloc failed (%s)", cudaGetErrorString(cudaGetLastError()));
+        }
+        O.m[k] = R.media[k];
+    }
+    dim3 blk(64, 4);
+    dim3 grid((M.G.dim[2] + blk.x - 1) / blk.x, (M.G.dim[1] + blk.y - 1) / blk.y, M.G.dim[0]);
+    media_pointwise<<<grid, blk, 0, st>>>(in[0], in[1], in[2], O, M.G);
+    media_averaged<<<grid, blk, 0, st>>>(O, M.G);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return fail("heterogeneous media: kernels failed (%s)", cudaGetErrorString(e));
     return 0;
 }
 
@@ -1111,9 +1285,14 @@ int opesci_b200_configure(const OpesciB200Params *params)
         }
     if (params->kind == OPESCI_KIND_STAGGERED_ELASTIC) {
         if (params->nfields != 9 || params->nlevels != 2) return fail("staggered: need 9 fields, 2 levels");
+        if (params->hetero) {
+            if (params->is_double) return fail("heterogeneous media: fp32 only (the reference reader is float*)");
+            memcpy(M.hc.c, params->h_c, sizeof M.hc.c);
+            memcpy(M.hc.c2, params->h_c2, sizeof M.hc.c2);
+        }
         if (params->free_surface == 1) {
             if (params->so != 4) return fail("Levander free surface needs so == 4");
-            build_levander(M);
+            if (params->hetero) build_levander_hetero(M); else build_levander(M);
         }
     } else if (params->kind == OPESCI_KIND_REGULAR_ACOUSTIC) {
         if (params->nfields != 1 || params->nlevels != 3) return fail("regular: need 1 field, 3 levels");
@@ -1147,6 +1326,7 @@ int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
         // regulargrid.py:489-490 allocates without clearing; de-facto contract "buffers start as 0"
         if (cudaMemsetAsync(R->dev[f], 0, R->bytes_per_field, st) != cudaSuccess) return bail(fail("cudaMemset failed"));
     }
+    if (setup_media(*R, st)) return bail(1);
     if (upload_programs(*R)) return bail(1);
     if (setup_fused(*R)) return bail(1);
     double secs = 0.0;
@@ -1258,6 +1438,15 @@ int opesci_b200_comm_init(int rank, int nranks, const void *id_bytes, int nbytes
     NCCL_OK(g_nccl.CommInitRank(&g_nccl.comm, nranks, id, rank));
     g_nccl.rank = rank;
     g_nccl.nranks = nranks;
+    return 0;
+}
+
+int opesci_b200_slab_range(int rank, int nranks, int gdim1, int so, int *L0, int *L1)
+{
+    OpesciSlab sl;
+    if (opesci_slab_make(&sl, rank, nranks, gdim1, so / 2, OPESCI_SLAB_HALO)) return fail("opesci_b200_slab_range: slabs thinner than the halo");
+    if (L0) *L0 = sl.L0;
+    if (L1) *L1 = sl.L1;
     return 0;
 }
 

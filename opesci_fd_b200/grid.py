@@ -79,6 +79,11 @@ class Grid(object):
                        c_velocity=arr(p.c_velocity, 3, 3, m),
                        lev_stress=arr(p.lev_stress, 3, 3, 3, 2),
                        lev_vnormal=arr(p.lev_vnormal, 3, 3), lev_vtang=arr(p.lev_vtang, 3, 3))
+            if p.hetero:
+                out.update(hetero=1, media_files=[self.rho_file, self.vp_file, self.vs_file],
+                           h_c=arr(p.h_c, 3, m), h_c2=arr(p.h_c2, 3, m), h_lev_den=arr(p.h_lev_den, 3, 2),
+                           h_lev_own=arr(p.h_lev_own, 3, 3, 2), h_lev_oth=arr(p.h_lev_oth, 3, 3, 2),
+                           h_vn=arr(p.h_vn, 3, 2))
         else:
             out.update(ac_coef=arr(p.ac_coef, 3, m), ac_centre=float(p.ac_centre),
                        ac_init_coef=arr(p.ac_init_coef, 3, m), ac_init_centre=float(p.ac_init_centre),

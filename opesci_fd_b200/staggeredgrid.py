@@ -15,12 +15,15 @@ and lowers the model to the literal tables the generated code would have contain
 """
 from fractions import Fraction
 
-from sympy import Symbol
+import numpy as np
+from sympy import Symbol, expand
 
 from . import abi, cexpr
 from .codeprinter import ccode, literal
 from .derivative import DDerivative
-from .fields import SField, VField
+from .fields import Media, SField, VField
+from sympy import IndexedBase
+
 from .regulargrid import RegularGrid, _frac, _same_field
 from .util import staggered_first_weights
 
@@ -100,8 +103,17 @@ class StaggeredGrid(RegularGrid):
         """reference: staggeredgrid.py:234-282"""
         self.read = read
         if self.read:
-            raise NotImplementedError("heterogeneous media (read=True): the reference's own output for "
-                                      "this mode is NaN (SURVEY.md 0.8); not lowered in this round")
+            # rho, vp, vs come from flat float32 files (opesci_read_simple_binary_ptr); the derived arrays
+            # beta, beta1-3, lambda, mu, mu12/13/23 are computed by the library on the device
+            self.rho_file, self.vp_file, self.vs_file = rho_file, vp_file, vs_file
+            kw = dict(dimension=3, staggered=[False, False, False], index=self.index)
+            self.rho, self.vp, self.vs = Media('rho', **kw), Media('vp', **kw), Media('vs', **kw)
+            self.beta = [Media(n, **kw) for n in ('beta', 'beta1', 'beta2', 'beta3')]
+            self.lam = Media('lambda', **kw)
+            self.mu = [Media(n, **kw) for n in ('mu', 'mu12', 'mu13', 'mu23')]
+            self.media_arrays = None      # optional (rho, vp, vs) numpy arrays instead of files
+            self.media_plane0 = 0         # slab runs: first global x plane held by media_arrays
+            return
         self.set_variable('rho', rho, 'float', True)
         self.set_variable('beta', 1.0 / rho, 'float', True)
         self.set_variable('lambda', rho * (vp ** 2 - 2 * vs ** 2), 'float', True)
@@ -163,6 +175,29 @@ class StaggeredGrid(RegularGrid):
                     "general PDEs are SURVEY.md 8f item 4)" % field.label)
             self.pde[str(field.label)] = table
 
+    def set_media_arrays(self, rho, vp, vs, plane0=0):
+        """B200 addition: hand the medium over as float32 arrays [nplanes][dim2][dim3] (same layout as
+        the files) holding the global x planes [plane0, plane0+nplanes) -- a slab rank only needs its
+        own planes (opesci_b200_slab_range)."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (rho, vp, vs)]
+        self.media_arrays, self.media_plane0 = arrs, int(plane0)
+
+    def _load_media(self):
+        dims = [self.dim[d].value for d in range(3)]
+        if self.media_arrays is None:
+            n = dims[0] * dims[1] * dims[2]
+            arrs = []
+            for fn in (self.rho_file, self.vp_file, self.vs_file):
+                a = np.fromfile(fn, dtype='<f4', count=n)     # opesciIO.cpp:319: flat float32
+                if a.size != n:
+                    raise IOError("%s: expected %d float32 values, found %d" % (fn, n, a.size))
+                arrs.append(np.ascontiguousarray(a.reshape(dims), dtype=np.float32))
+            self.media_arrays, self.media_plane0 = arrs, 0
+        for a in self.media_arrays:
+            if a.ndim != 3 or list(a.shape[1:]) != dims[1:]:
+                raise ValueError("media arrays must be [nplanes][dim2][dim3] = [*][%d][%d]" % (dims[1], dims[2]))
+        return self.media_arrays
+
     def set_free_surface_boundary(self, dimension, side):
         """reference: staggeredgrid.py:214-232.  Levander for so == 4, Robertsson otherwise."""
         self._free_surface.add((dimension, side))
@@ -221,20 +256,26 @@ class StaggeredGrid(RegularGrid):
             for k in range(m):
                 dst[k] = literal(float(ck[k] * dt / dx[d] * coef))
 
+        if self.read:
+            self._lower_hetero(p, keep, vel, normal, shear, ck, dt, dx, m, so, pde)
         # interior updates
         M = {}
         for a in (1, 2, 3):
+            if self.read:
+                break
             for d in (1, 2, 3):
                 M[(a, d)] = val(pde(normal[a], vel[d], d))
                 fill(p.c_stress_normal[a - 1][d - 1], M[(a, d)], d)
                 g = normal[a] if a == d else shear[tuple(sorted((a, d)))]
                 fill(p.c_velocity[a - 1][d - 1], val(pde(vel[a], g, d)), d)
         for s, (a, b) in enumerate(_SHEAR):
+            if self.read:
+                break
             fill(p.c_stress_shear[s][0], val(pde(shear[(a, b)], vel[a], b)), b)
             fill(p.c_stress_shear[s][1], val(pde(shear[(a, b)], vel[b], a)), a)
         # Levander free surface (so == 4): eliminate d_d V_d with T_dd' = 0 (fields.py:313-353)
         # and build the ghost velocities from 2nd-order differences (fields.py:208-242)
-        if so == 4:
+        if so == 4 and not self.read:
             for d in (1, 2, 3):
                 for e in (1, 2, 3):
                     if e == d:
@@ -265,6 +306,71 @@ class StaggeredGrid(RegularGrid):
             ivars = self._solution_variables(coords)
             fvars = self._solution_variables(coords)
             fvars.field('__F__', cexpr.DOUBLE if self.double else cexpr.FLOAT)
-            self._field_spec(p, k, field, lo, hi, lo, hi, ccode(field.sol.subs(self.t, t0)), ivars,
-                             self._residual_text(field, ti, tn, loop), fvars, keep)
+            if self.read:
+                for v in (ivars, fvars):
+                    for mid, name in enumerate(abi.MEDIA_NAMES):
+                        v.media(name, cexpr.FLOAT, mid)
+                init_text = ccode(self._read_solution(field.sol.subs(self.t, t0), loop))
+                placeholder = IndexedBase(str(field.label))[[ti] + loop]
+                final_text = ccode(placeholder - self._read_solution(field.sol.subs(self.t, tn), loop))
+                final_text = final_text.replace(ccode(placeholder), '__F__')
+            else:
+                init_text = ccode(field.sol.subs(self.t, t0))
+                final_text = self._residual_text(field, ti, tn, loop)
+            self._field_spec(p, k, field, lo, hi, lo, hi, init_text, ivars, final_text, fvars, keep)
         return p, keep
+
+    def _read_solution(self, sol, loop):
+        """`read` mode (reference: staggeredgrid.py:648-653): beta, lambda, mu become the per-cell arrays
+        and the index symbols x,y,z become the INTEGER loop variables _x,_y,_z -- also where the
+        solution meant them as coordinates."""
+        sol = sol.subs({Symbol('beta'): self.beta[0][tuple(loop)], Symbol("lambda"): self.lam[tuple(loop)],
+                        Symbol("mu"): self.mu[0][tuple(loop)]})
+        for idx, l in zip(self.index, loop):
+            sol = sol.subs(idx, l)
+        return sol
+
+    def _lower_hetero(self, p, keep, vel, normal, shear, ck, dt, dx, m, so, pde):
+        """Heterogeneous (`read`) lowering: check that the PDE coefficients are exactly the isotropic
+        elastic ones (lambda+2mu, lambda, mu, beta) and emit the media-free literals of
+        `literal*G[...]*media[x][y][z]` plus the Levander tables."""
+        if self.double:
+            raise NotImplementedError("heterogeneous media: fp32 only (the reference reader is float*)")
+        beta, lam, mu = Symbol('beta'), Symbol('lambda'), Symbol('mu')
+
+        def same(a, b):
+            return expand(a - b) == 0
+        for a in (1, 2, 3):
+            for d in (1, 2, 3):
+                ok = same(pde(normal[a], vel[d], d), lam + 2 * mu if a == d else lam)
+                g = normal[a] if a == d else shear[tuple(sorted((a, d)))]
+                ok = ok and same(pde(vel[a], g, d), beta)
+                if not ok:
+                    raise NotImplementedError("heterogeneous media: isotropic elastic PDEs only")
+        for (a, b) in _SHEAR:
+            if not (same(pde(shear[(a, b)], vel[a], b), mu) and same(pde(shear[(a, b)], vel[b], a), mu)):
+                raise NotImplementedError("heterogeneous media: isotropic elastic PDEs only")
+        p.hetero = 1
+        for d in (1, 2, 3):
+            for k in range(m):
+                p.h_c[d - 1][k] = literal(float(ck[k] * dt / dx[d]))
+                p.h_c2[d - 1][k] = literal(float(2 * ck[k] * dt / dx[d]))
+        P = {d: dx[1] * dx[2] * dx[3] / dx[d] for d in (1, 2, 3)}
+        for d in (1, 2, 3):
+            p.h_vn[d - 1][0] = literal(float(P[d]))
+            p.h_vn[d - 1][1] = literal(float(2 * P[d]))
+            if so != 4:
+                continue
+            p.h_lev_den[d - 1][0] = literal(float(12 * P[d]))
+            p.h_lev_den[d - 1][1] = literal(float(24 * P[d]))
+            for f in (1, 2, 3):
+                for k in range(2):
+                    p.h_lev_own[d - 1][f - 1][k] = literal(float(48 * P[d] * ck[k] * dt / dx[f]))
+                    p.h_lev_oth[d - 1][f - 1][k] = literal(float(24 * P[d] * ck[k] * dt / dx[f]))
+                if f != d:
+                    p.lev_vtang[d - 1][f - 1] = literal(float(dx[d] / dx[f]))
+        arrs = self._load_media()
+        p.media_plane0, p.media_nplanes = self.media_plane0, arrs[0].shape[0]
+        fptr = abi.POINTER(abi.c_float)
+        p.rho, p.vp, p.vs = [a.ctypes.data_as(fptr) for a in arrs]
+        keep += arrs

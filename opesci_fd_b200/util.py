@@ -142,3 +142,19 @@ def shift_index(expr, k, s):
         idx[k] += s
         return Indexed(expr.base, *idx)
     return expr.func(*[shift_index(a, k, s) for a in expr.args])
+
+
+def synthetic_media(dims, seed=20261017):
+    """Synthetic heterogeneous medium for `read` mode: rho, vp, vs i.i.d.
+    uniform per cell from a counter-based generator (numpy Philox), rho in [1.0,1.5),
+    vp in [1.0,1.5), vs in [0.4,0.7) -- keeps lambda = rho*(vp^2 - 2 vs^2) > 0 and mu > 0.
+    Returns three float32 arrays of shape `dims` (the file layout of
+    opesci_read_simple_binary_ptr: flat little-endian float32, dim1*dim2*dim3 values,
+    reference: opesci/staggeredgrid.py:549-551)."""
+    import numpy as np
+    gen = np.random.Generator(np.random.Philox(seed))
+    n = int(np.prod(dims))
+    rho = (1.0 + 0.5 * gen.random(n, dtype=np.float32)).astype(np.float32).reshape(dims)
+    vp = (1.0 + 0.5 * gen.random(n, dtype=np.float32)).astype(np.float32).reshape(dims)
+    vs = (0.4 + 0.3 * gen.random(n, dtype=np.float32)).astype(np.float32).reshape(dims)
+    return rho, vp, vs

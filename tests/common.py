@@ -28,7 +28,15 @@ def make_grid(cfg, flags=None):
     """cfg: dict with kind, so, grid_size, dt, steps, double, domain[, rho, vp, vs]."""
     so = cfg["so"]
     order = [2, so, so, so]
-    if cfg["kind"] == "eigenwave3d":
+    if cfg["kind"] == "eigenwave3d_read":
+        # heterogeneous `read` mode: the same synthetic medium the patched reference read from files
+        import eigenwave3d as drv
+        from opesci_fd_b200.util import synthetic_media
+        g = drv.eigenwave3d(tuple(cfg["domain"]), tuple(cfg["grid_size"]), cfg["dt"], cfg["dt"] * cfg["steps"],
+                            accuracy_order=order, o_converge=False, read=True, rho_file="rho", vp_file="vp",
+                            vs_file="vs", verbose=False)
+        g.set_media_arrays(*synthetic_media([d.value for d in g.dim], cfg["seed"]))
+    elif cfg["kind"] == "eigenwave3d":
         import eigenwave3d as drv
         g = drv.eigenwave3d(tuple(cfg["domain"]), tuple(cfg["grid_size"]), cfg["dt"], cfg["dt"] * cfg["steps"],
                             accuracy_order=order, o_converge=True, double=cfg["double"],

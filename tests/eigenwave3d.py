@@ -4,7 +4,8 @@ on the B200 library.  Usage:  python tests/eigenwave3d.py default -so 4 -c g++ -
 
 Differences to the reference driver: `--compiler` only selects a Compiler object (nothing is
 compiled per model), `--pluto/--tile/--fission/--papi-events` are accepted and ignored (CPU loop
-transformations), `read` mode raises.
+transformations); `read` mode follows the PATCHED reference semantics (SURVEY.md 0.8:
+the unpatched reference produces NaN) and `--synthetic` replaces its absent data files.
 """
 import os
 import sys
@@ -123,10 +124,34 @@ def default(compiler=None, execute=False, nthreads=1, accuracy_order=[2, 4, 4, 4
     return out
 
 
-def read_data(**kwargs):
-    """reference: tests/eigenwave3d.py:201-228 -- heterogeneous media from files."""
-    raise NotImplementedError("`read` mode: the reference's own output is NaN (SURVEY.md 0.8); "
-                              "not part of this round")
+def read_data(compiler=None, execute=False, nthreads=1, accuracy_order=[2, 4, 4, 4], output=False,
+              profiling=False, papi_events=[], fission=False, synthetic=False):
+    """Model initialisation from input files: heterogeneous rho / vp / vs, 200^3 arrays at so=4
+    (reference: tests/eigenwave3d.py:201-228).  The reference's data files RHOhomogx200, VPhomogx200,
+    VShomogx200 are not in its repository; `synthetic=True` (CLI: --synthetic) substitutes the random
+    medium of SURVEY.md 8d config 5."""
+    domain_size = (1.0, 1.0, 1.0)
+    grid_size = (195, 195, 195)
+    dt = 0.002
+    tmax = 1.0
+    os.makedirs(_test_dir, exist_ok=True)
+    filename = path.join(_test_dir, 'eigenwave3d_read.json')
+    grid = eigenwave3d(domain_size, grid_size, dt, tmax, read=True, accuracy_order=accuracy_order,
+                       o_converge=False, omp=True, simd=False, ivdep=True, filename=filename,
+                       rho_file='RHOhomogx200', vp_file='VPhomogx200', vs_file='VShomogx200', fission=fission)
+    grid.set_switches(output_vts=output, profiling=profiling)
+    grid.set_papi_events(papi_events)
+    if synthetic:
+        from opesci_fd_b200.util import synthetic_media
+        grid.set_media_arrays(*synthetic_media([d.value for d in grid.dim]))
+    if compiler is None:
+        grid.generate(filename)
+    else:
+        grid.compile(filename, compiler=compiler, shared=False)
+    if execute:
+        grid.execute(filename, compiler=compiler or 'g++', nthreads=nthreads)
+        grid.convergence()
+    return grid
 
 
 def converge_test(execute=True):
@@ -150,7 +175,8 @@ def main():
     ModeHelp = """Avalable testing modes:
 default:   Eigenwave test case on a unit cube grid (100 x 100 x 100)
 
-read:      Test for model intialisation from input file (not available on the B200 path)
+read:      Test for model intialisation from input file (RHOhomogx200, VPhomogx200, VShomogx200 in the
+           working directory, or --synthetic)
 
 converge:  Convergence test of the (2,4) scheme, which is 2nd order
            in time and 4th order in space. The test halves spacing
@@ -175,6 +201,8 @@ converge:  Convergence test of the (2,4) scheme, which is 2nd order
     p.add_argument('--pluto', action='store_true', default=False, help='(accepted, ignored)')
     p.add_argument('--fission', action='store_true', default=False, help='(accepted, ignored)')
     p.add_argument('--double', action='store_true', default=False, help='use double precision fields')
+    p.add_argument('--synthetic', action='store_true', default=False,
+                   help='read mode: use the synthetic random medium instead of the data files')
     args = p.parse_args()
     print("Eigenwave3D example (mode=%s)" % args.mode)
 
@@ -183,7 +211,8 @@ converge:  Convergence test of the (2,4) scheme, which is 2nd order
                 accuracy_order=[2, args.so, args.so, args.so], profiling=args.profiling,
                 double=args.double)
     elif args.mode == 'read':
-        read_data()
+        read_data(compiler=args.compiler, execute=args.execute, nthreads=args.nthreads,
+                  accuracy_order=[2, args.so, args.so, args.so], profiling=args.profiling, synthetic=args.synthetic)
     elif args.mode == 'converge':
         converge_test()
     elif args.mode == 'cx1':

@@ -7,9 +7,12 @@ in a fresh process, dumps all fields (all time levels) and stores them losslessl
 
   tests/golden/<name>.npz      fields [nfields][nlevels][dim1][dim2][dim3] (raw bits) + printed L2 norms
   tests/golden/norms.json      printed L2 norms of the `default` / `mid` configurations
+  tests/golden/hashes.json     sha256 of the raw bits of every field of the `heteromid` configurations
+                               (fields too large to commit)
   tests/golden/literals.json   every float literal of the interior kernels as printed in the
                                generated source (pins the host front end's coefficient tables)
 """
+import hashlib
 import json
 import os
 import re
@@ -29,7 +32,7 @@ def run(cfg, dump=None):
         nelem = cfg["nlevels"] * int(np.prod(cfg["dim"]))
         cmd += ["--dump", dump, str(nelem)]
     env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
-    out = subprocess.check_output(cmd, env=env).decode()
+    out = subprocess.check_output(cmd, env=env, cwd=ROOT).decode()
     return [float(m.group(1)) for m in re.finditer(r"^L2\[\d+\] \S+ (\S+)$", out, re.M)], \
            [m.group(1) for m in re.finditer(r"^L2\[\d+\] (\S+) \S+$", out, re.M)]
 
@@ -48,10 +51,20 @@ def kernel_literals(cfg):
 
 
 def main():
-    norms, literals = {}, {}
+    norms, literals, hashes = {}, {}, {}
     for name, cfg in sorted(MAN.items()):
         tags = set(cfg["tags"])
-        if "small" in tags:
+        if "heteromid" in tags:
+            dump = "/tmp/golden_%s.bin" % name
+            run(cfg, dump)
+            arr = np.fromfile(dump, dtype=np.float32).reshape(len(cfg["fields"]), cfg["nlevels"], *cfg["dim"])
+            os.remove(dump)
+            hashes[name] = dict(config={k: cfg[k] for k in ("kind", "so", "grid_size", "dt", "steps", "double",
+                                                            "domain", "dim", "fields", "seed")},
+                                sha256=[hashlib.sha256(arr[k].tobytes()).hexdigest() for k in range(arr.shape[0])],
+                                absmax=[float(np.abs(arr[k]).max()) for k in range(arr.shape[0])])
+            print("hashes", name, arr.shape)
+        elif "small" in tags:
             dump = "/tmp/golden_%s.bin" % name
             vals, printed = run(cfg, dump)
             dt = np.float64 if cfg["double"] else np.float32
@@ -70,6 +83,7 @@ def main():
                 norms[name]["config"].update(rho=cfg["rho"], vp=cfg["vp"], vs=cfg["vs"])
             literals[name] = kernel_literals(cfg)
             print("norms", name, printed[:2])
+    json.dump(hashes, open(os.path.join(HERE, "hashes.json"), "w"), indent=1, sort_keys=True)
     json.dump(norms, open(os.path.join(HERE, "norms.json"), "w"), indent=1, sort_keys=True)
     json.dump(literals, open(os.path.join(HERE, "literals.json"), "w"), indent=1, sort_keys=True)
 

@@ -63,6 +63,12 @@ def main():
 
     flags = os.environ.get("OPESCI_TEST_FLAGS")
     grid = make_grid(cfg, flags=int(flags) if (flags and use_cuda) else None)
+    if cfg["kind"] == "eigenwave3d_read":
+        # hand over only the planes this rank stores (its slab + halos), as a large run would
+        l0, l1 = ctypes.c_int(), ctypes.c_int()
+        assert lib.opesci_b200_slab_range(rank, world, grid.dim[0].value, cfg["so"], ctypes.byref(l0), ctypes.byref(l1)) == 0
+        rho, vp, vs = grid.media_arrays
+        grid.set_media_arrays(rho[l0.value:l1.value], vp[l0.value:l1.value], vs[l0.value:l1.value], plane0=l0.value)
     orig = grid.build_params
 
     def with_slab():

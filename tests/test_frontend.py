@@ -75,6 +75,36 @@ def test_lowered_staggered_literals_equal_generated_source(name):
         assert mine[field] == ref, "%s: literals of %s differ from the generated source" % (name, field)
 
 
+@pytest.mark.parametrize("name", sorted(n for n in LITERALS if n.startswith("ewh_")))
+def test_lowered_heterogeneous_literals_equal_generated_source(name):
+    """`read` mode: every term is literal*G*media; own-axis windows of the normal stresses carry a lambda
+    and a mu term per offset (literal c and 2c)."""
+    cfg = _config(name)
+    grid = make_grid(cfg)
+    p, keep = grid.build_params()
+    m = cfg["so"] // 2
+    assert p.hetero == 1
+
+    def window(c, fwd, c2=None):
+        c = [float(np.float32(x)) for x in c[:m]]
+        seq = c + [-x for x in c[1:]] + [-c[0]] if fwd else c[1:] + [-x for x in c] + [c[0]]
+        if c2 is None:
+            return seq
+        two = [float(np.float32(x)) for x in c2[:m]]
+        seq2 = two[1:] + [-x for x in two] + [two[0]]
+        return [v for pair in zip(seq, seq2) for v in pair]
+    mine = {}
+    for a, fname in enumerate(["Txx", "Tyy", "Tzz"]):
+        mine[fname] = sum((window(p.h_c[d], False, p.h_c2[d] if d == a else None) for d in range(3)), [])
+    for (a, b), fname in zip([(0, 1), (1, 2), (0, 2)], ["Txy", "Tyz", "Txz"]):
+        mine[fname] = window(p.h_c[b], True) + window(p.h_c[a], True)
+    for a, fname in enumerate(["U", "V", "W"]):
+        mine[fname] = sum((window(p.h_c[d], d == a) for d in range(3)), [])
+    for field, lits in LITERALS[name].items():
+        ref = [float(np.float32(float(x))) for x in lits]
+        assert mine[field] == ref, "%s: literals of %s differ from the generated source" % (name, field)
+
+
 @pytest.mark.parametrize("name", sorted(n for n in LITERALS if n.startswith("sw_")))
 def test_lowered_acoustic_literals_equal_generated_source(name):
     cfg = _config(name)
@@ -111,8 +141,15 @@ def test_cexpr_types_like_cxx():
 
 def test_unsupported_models_raise():
     import eigenwave3d as drv
+    # heterogeneous media are fp32 only (the reference's reader is float*), and the files must exist
+    h = drv.eigenwave3d((1.0, 1.0, 1.0), (10, 10, 10), 0.002, 0.01, accuracy_order=[2, 4, 4, 4], read=True,
+                        double=True, verbose=False)
     with pytest.raises(NotImplementedError):
-        drv.eigenwave3d((1.0, 1.0, 1.0), (10, 10, 10), 0.002, 0.01, accuracy_order=[2, 4, 4, 4], read=True, verbose=False)
+        h.build_params()
+    h = drv.eigenwave3d((1.0, 1.0, 1.0), (10, 10, 10), 0.002, 0.01, accuracy_order=[2, 4, 4, 4], read=True,
+                        rho_file="/nonexistent/rho", vp_file="/nonexistent/vp", vs_file="/nonexistent/vs", verbose=False)
+    with pytest.raises((IOError, OSError)):
+        h.build_params()
     g = drv.eigenwave3d((1.0, 1.0, 1.0), (10, 10, 10), 0.002, 0.01, accuracy_order=[2, 4, 4, 4], verbose=False)
     g._free_surface.discard((3, 1))
     with pytest.raises(NotImplementedError):

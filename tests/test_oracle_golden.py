@@ -8,7 +8,13 @@ staggered (Levander at so=4, Robertsson otherwise) and regular grids.
 import numpy as np
 import pytest
 
-from common import bits, fields_of, golden_names, load_golden, make_grid
+import hashlib
+import json
+import os
+
+from common import GOLDEN, bits, fields_of, golden_names, load_golden, make_grid
+
+HASHES = json.load(open(os.path.join(GOLDEN, "hashes.json")))
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -22,6 +28,9 @@ def test_oracle_bit_exact_vs_reference_golden(name, oracle_lib):
     for k, fname in enumerate(cfg["fields"]):
         nbad = int((bits(mine[k]) != bits(ref_fields[k])).sum())
         assert nbad == 0, "%s: %d cells differ from the reference's generated code" % (fname, nbad)
+    if cfg["kind"] == "eigenwave3d_read":
+        grid.free()   # `read` mode runs with converge=False: the reference prints no norms
+        return
     # reference-faithful norm arithmetic (serial accumulation in real_t): same printed digits
     norms = grid.convergence()
     got = np.array([norms["%s_l2" % f] for f in cfg["fields"]])
@@ -29,4 +38,19 @@ def test_oracle_bit_exact_vs_reference_golden(name, oracle_lib):
     # the double-accumulated norms (what the CUDA library reports) agree to accumulation error
     got64 = np.array(grid.convergence_f64())
     np.testing.assert_allclose(got64, ref_l2, rtol=2e-5 if not cfg["double"] else 2e-9)  # golden norms carry 10 digits
+    grid.free()
+
+
+@pytest.mark.parametrize("name", sorted(HASHES))
+def test_oracle_bit_exact_vs_patched_reference_hashes(name, oracle_lib):
+    """Heterogeneous `read` mode at 48x40x44 cells x 40 steps (random rho/vp/vs per cell): the fields are too
+    large to commit, so the fixture holds the sha256 of the raw bits of every field as produced by the
+    patched reference (oracle/refgen/make_ref.py)."""
+    entry = HASHES[name]
+    grid = make_grid(entry["config"])
+    grid.run(library=oracle_lib)
+    mine = fields_of(grid)
+    assert not np.isnan(mine).any()
+    got = [hashlib.sha256(mine[k].tobytes()).hexdigest() for k in range(mine.shape[0])]
+    assert got == entry["sha256"]
     grid.free()

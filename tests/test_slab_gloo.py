@@ -24,10 +24,11 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize("world,so", [(2, 4), (3, 4), (2, 2)])
-def test_slab_decomposition_is_bit_exact(world, so, oracle_lib, tmp_path):
-    cfg = dict(kind="eigenwave3d", so=so, grid_size=[30 * world, 11, 9], dt=0.002, steps=11, double=False,
-               domain=[1.0 * world, 0.9, 0.8], rho=1.2, vp=1.6, vs=0.8)
+@pytest.mark.parametrize("world,so,kind", [(2, 4, "eigenwave3d"), (3, 4, "eigenwave3d"), (2, 2, "eigenwave3d"),
+                                           (2, 4, "eigenwave3d_read")])
+def test_slab_decomposition_is_bit_exact(world, so, kind, oracle_lib, tmp_path):
+    cfg = dict(kind=kind, so=so, grid_size=[30 * world, 11, 9], dt=0.002, steps=11, double=False,
+               domain=[1.0 * world, 0.9, 0.8], rho=1.2, vp=1.6, vs=0.8, seed=11)
     single = make_grid(cfg)
     single.run(library=oracle_lib)
     ref = fields_of(single)
