@@ -234,8 +234,15 @@ def main():
         # two-pass path: the stress kernel dominates; its own compulsory traffic is 9 reads + 6 writes
         dom_name, dom_ms, dom_bytes = "stress_interior (two-pass path: 15 words/pt)", kms[0], 60.0 * pts_gpu
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture
+    # (profiles/r01_fused_v3_ncu_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum); only known for
+    # the configuration that capture was taken on
+    traffic = None
+    if fused and world == 1 and n == 1024:
+        traffic = 50.116791e9 + 39.147999e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": dom_name, "kernel_ms": dom_ms, "peak_source": peak_src,
+                "traffic": traffic, "algorithmic_bytes_per_launch": dom_bytes,
+                "kernel": dom_name, "kernel_ms": dom_ms, "peak_source": peak_src,
                 "step_algorithmic_GBps": value / world * BYTES_PER_POINT,
                 "step_frac_of_peak": value / world * BYTES_PER_POINT / peak,
                 "kernel_ms_breakdown": {"stress_or_fused": kms[0], "velocity": kms[1], "ghost_loops": kms[2]},

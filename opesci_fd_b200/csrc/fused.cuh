@@ -26,6 +26,7 @@
 #pragma once
 #include <cuda.h>
 
+#include "hetero.cuh"
 #include "kernels.cuh"
 
 namespace opesci {
@@ -94,6 +95,32 @@ __device__ __forceinline__ T window_fast_arr(const T *v, const float *c)
     return d;
 }
 
+// heterogeneous mode: every term is (c*g)*media; NV = 2 emits the lambda term then the mu term (c2) per offset
+template <int M, bool FWD, int NV>
+__device__ __forceinline__ void window_ref_arr_h(float &acc, bool &first, const float *v, const float *c, const float *c2,
+                                                 float med, float med2)
+{
+#define OPESCI_EMIT(idx, sgn, k)                                   \
+    {                                                              \
+        term_h(acc, first, (sgn) * c[k], v[idx], med);             \
+        if (NV == 2) term_h(acc, first, (sgn) * c2[k], v[idx], med2); \
+    }
+    if (FWD) {
+#pragma unroll
+        for (int o = 1; o <= M; ++o) OPESCI_EMIT(o + M - 1, 1.0f, o - 1)
+#pragma unroll
+        for (int o = 1; o <= M - 1; ++o) OPESCI_EMIT(-o + M - 1, -1.0f, o)
+        OPESCI_EMIT(M - 1, -1.0f, 0)
+    } else {
+#pragma unroll
+        for (int o = 1; o <= M - 1; ++o) OPESCI_EMIT(o + M, 1.0f, o)
+#pragma unroll
+        for (int o = 1; o <= M; ++o) OPESCI_EMIT(-o + M, -1.0f, o - 1)
+        OPESCI_EMIT(M, 1.0f, 0)
+    }
+#undef OPESCI_EMIT
+}
+
 template <int M> struct FusedCfg {
     static constexpr int EZ = 64, EY = 16;                 // threads = stress tile (incl. recomputed halo)
     // stored tile.  TMA needs the innermost box coordinate 16-B aligned (measured on B200: an
@@ -114,6 +141,8 @@ struct FusedArgs {
     FieldPtrs F;
     GridGeom G;
     StaggeredCoefs C;
+    MediaPtrs MD;     // heterogeneous mode (HET kernels): per-cell media, +32 B/point of read traffic
+    HeteroCoefs HC;
     int t0, t1;
     int xchunk;       // planes per x-chunk
     // Tile subset of this launch.  The tiles inside the box [box_lo, box_hi) (tile_y, tile_z, chunk)
@@ -169,7 +198,7 @@ __device__ __forceinline__ void gstore2(float *p, float a, float b)
 // along y and x is one 8-byte access for both points and the z-windows of both come from three
 // 8-byte loads, which halves the load/store-unit instruction count (the busiest pipe of the
 // one-point-per-thread version, ncu: profiles/r01_fused_v2_ncu_summary.txt).
-template <int SO, int ARITH>
+template <int SO, int ARITH, bool HET = false>
 __global__ void __launch_bounds__(FusedCfg<SO / 2>::THREADS, 1)
 fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
            const __grid_constant__ CUtensorMap tmW, const FusedArgs A)
@@ -341,6 +370,17 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             load6(pv, fv);
             load6(pw, fw);
             T tn[2][6], uself[2], vself_next[2], wself_next[2];
+            // heterogeneous mode: lambda, mu, mu12, mu23, mu13 of the two cells (plane xs)
+            T med[2][5];
+            if (HET) {
+                const int ids[5] = {OPESCI_MEDIA_LAMBDA, OPESCI_MEDIA_MU, OPESCI_MEDIA_MU12, OPESCI_MEDIA_MU23, OPESCI_MEDIA_MU13};
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const float *mp = A.MD.m[ids[k]] + pyz + px;
+                    if (inb2) { const float2 v = *reinterpret_cast<const float2 *>(mp); med[0][k] = v.x; med[1][k] = v.y; }
+                    else { med[0][k] = inb[0] ? mp[0] : 0.f; med[1][k] = inb[1] ? mp[1] : 0.f; }
+                }
+            }
 #pragma unroll
             for (int L = 0; L < 2; ++L) {
                 T wz_b[2 * M], uz_f[2 * M], vz_f[2 * M];
@@ -353,7 +393,49 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                 uself[L] = ux[L][0];               // U[t0] at plane xs-M (velocity self term of this iteration)
                 vself_next[L] = vx[L][0];          // V,W[t0] at plane xs-M+1
                 wself_next[L] = wx[L][0];
-                if (ARITH == OPESCI_ARITH_REFERENCE) {
+                if (HET && ARITH == OPESCI_ARITH_REFERENCE) {
+                    const float lam = med[L][0], mu = med[L][1];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        T acc = told[L][a];
+                        bool first = false;
+                        if (a == 0) window_ref_arr_h<M, false, 2>(acc, first, ux[L], A.HC.c[0], A.HC.c2[0], lam, mu);
+                        else window_ref_arr_h<M, false, 1>(acc, first, ux[L], A.HC.c[0], A.HC.c2[0], lam, mu);
+                        if (a == 1) window_ref_arr_h<M, false, 2>(acc, first, vy_b[L], A.HC.c[1], A.HC.c2[1], lam, mu);
+                        else window_ref_arr_h<M, false, 1>(acc, first, vy_b[L], A.HC.c[1], A.HC.c2[1], lam, mu);
+                        if (a == 2) window_ref_arr_h<M, false, 2>(acc, first, wz_b, A.HC.c[2], A.HC.c2[2], lam, mu);
+                        else window_ref_arr_h<M, false, 1>(acc, first, wz_b, A.HC.c[2], A.HC.c2[2], lam, mu);
+                        tn[L][a] = acc;
+                    }
+                    {
+                        T acc = told[L][3]; bool first = false;   // Txy (mu12): D_y U, D_x V
+                        window_ref_arr_h<M, true, 1>(acc, first, uy_f[L], A.HC.c[1], A.HC.c2[1], med[L][2], 0.f);
+                        window_ref_arr_h<M, true, 1>(acc, first, vx[L], A.HC.c[0], A.HC.c2[0], med[L][2], 0.f);
+                        tn[L][3] = acc;
+                    }
+                    {
+                        T acc = told[L][4]; bool first = false;   // Tyz (mu23): D_z V, D_y W
+                        window_ref_arr_h<M, true, 1>(acc, first, vz_f, A.HC.c[2], A.HC.c2[2], med[L][3], 0.f);
+                        window_ref_arr_h<M, true, 1>(acc, first, wy_f[L], A.HC.c[1], A.HC.c2[1], med[L][3], 0.f);
+                        tn[L][4] = acc;
+                    }
+                    {
+                        T acc = told[L][5]; bool first = false;   // Txz (mu13): D_z U, D_x W
+                        window_ref_arr_h<M, true, 1>(acc, first, uz_f, A.HC.c[2], A.HC.c2[2], med[L][4], 0.f);
+                        window_ref_arr_h<M, true, 1>(acc, first, wx[L], A.HC.c[0], A.HC.c2[0], med[L][4], 0.f);
+                        tn[L][5] = acc;
+                    }
+                } else if (HET) {
+                    const T du = window_fast_arr<M, T, false>(ux[L], A.HC.c[0]), dv = window_fast_arr<M, T, false>(vy_b[L], A.HC.c[1]),
+                            dw = window_fast_arr<M, T, false>(wz_b, A.HC.c[2]);
+                    const T tr = med[L][0] * (du + dv + dw), mu2 = 2.0f * med[L][1];
+                    tn[L][0] = told[L][0] + (tr + mu2 * du);
+                    tn[L][1] = told[L][1] + (tr + mu2 * dv);
+                    tn[L][2] = told[L][2] + (tr + mu2 * dw);
+                    tn[L][3] = told[L][3] + med[L][2] * (window_fast_arr<M, T, true>(uy_f[L], A.HC.c[1]) + window_fast_arr<M, T, true>(vx[L], A.HC.c[0]));
+                    tn[L][4] = told[L][4] + med[L][3] * (window_fast_arr<M, T, true>(vz_f, A.HC.c[2]) + window_fast_arr<M, T, true>(wy_f[L], A.HC.c[1]));
+                    tn[L][5] = told[L][5] + med[L][4] * (window_fast_arr<M, T, true>(uz_f, A.HC.c[2]) + window_fast_arr<M, T, true>(wx[L], A.HC.c[0]));
+                } else if (ARITH == OPESCI_ARITH_REFERENCE) {
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
                         T acc = told[L][a];
@@ -462,6 +544,15 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                 load6(syz, fyz);
                 load6(szz, fzz);
                 T vout[2][3];
+                T bet[2][3];   // heterogeneous mode: beta1, beta2, beta3 of the two cells (plane xv)
+                if (HET) {
+                    const long long pxv_ = px - (long long)(M + 1) * sx;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float2 v = *reinterpret_cast<const float2 *>(A.MD.m[OPESCI_MEDIA_BETA1 + k] + pyz + pxv_);
+                        bet[0][k] = v.x; bet[1][k] = v.y;
+                    }
+                }
 #pragma unroll
                 for (int L = 0; L < 2; ++L) {
                     T xz_zb[2 * M], yz_zb[2 * M], zz_zf[2 * M];
@@ -473,7 +564,30 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                     }
                     // x-windows from registers: Txx fwd = planes xv-M+1..xv+M = txx[0..2M-1];
                     // Txy, Txz bwd = planes xv-M..xv+M-1 = txy[0..2M-1]
-                    if (ARITH == OPESCI_ARITH_REFERENCE) {
+                    if (HET && ARITH == OPESCI_ARITH_REFERENCE) {
+                        T acc = 0; bool first = true;
+                        window_ref_arr_h<M, true, 1>(acc, first, txx[L], A.HC.c[0], A.HC.c2[0], bet[L][0], 0.f);
+                        window_ref_arr_h<M, false, 1>(acc, first, xy_yb[L], A.HC.c[1], A.HC.c2[1], bet[L][0], 0.f);
+                        window_ref_arr_h<M, false, 1>(acc, first, xz_zb, A.HC.c[2], A.HC.c2[2], bet[L][0], 0.f);
+                        vout[L][0] = add_rn<T>(acc, uself[L]);
+                        acc = 0; first = true;
+                        window_ref_arr_h<M, false, 1>(acc, first, txy[L], A.HC.c[0], A.HC.c2[0], bet[L][1], 0.f);
+                        window_ref_arr_h<M, true, 1>(acc, first, yy_yf[L], A.HC.c[1], A.HC.c2[1], bet[L][1], 0.f);
+                        window_ref_arr_h<M, false, 1>(acc, first, yz_zb, A.HC.c[2], A.HC.c2[2], bet[L][1], 0.f);
+                        vout[L][1] = add_rn<T>(acc, vself[L]);
+                        acc = 0; first = true;
+                        window_ref_arr_h<M, false, 1>(acc, first, txz[L], A.HC.c[0], A.HC.c2[0], bet[L][2], 0.f);
+                        window_ref_arr_h<M, false, 1>(acc, first, yz_yb[L], A.HC.c[1], A.HC.c2[1], bet[L][2], 0.f);
+                        window_ref_arr_h<M, true, 1>(acc, first, zz_zf, A.HC.c[2], A.HC.c2[2], bet[L][2], 0.f);
+                        vout[L][2] = add_rn<T>(acc, wself[L]);
+                    } else if (HET) {
+                        vout[L][0] = uself[L] + bet[L][0] * (window_fast_arr<M, T, true>(txx[L], A.HC.c[0]) + window_fast_arr<M, T, false>(xy_yb[L], A.HC.c[1]) +
+                                                             window_fast_arr<M, T, false>(xz_zb, A.HC.c[2]));
+                        vout[L][1] = vself[L] + bet[L][1] * (window_fast_arr<M, T, false>(txy[L], A.HC.c[0]) + window_fast_arr<M, T, true>(yy_yf[L], A.HC.c[1]) +
+                                                             window_fast_arr<M, T, false>(yz_zb, A.HC.c[2]));
+                        vout[L][2] = wself[L] + bet[L][2] * (window_fast_arr<M, T, false>(txz[L], A.HC.c[0]) + window_fast_arr<M, T, false>(yz_yb[L], A.HC.c[1]) +
+                                                             window_fast_arr<M, T, true>(zz_zf, A.HC.c[2]));
+                    } else if (ARITH == OPESCI_ARITH_REFERENCE) {
                         T acc = 0; bool first = true;
                         window_ref_arr<M, T, true>(acc, first, txx[L], A.C.v[0][0]);
                         window_ref_arr<M, T, false>(acc, first, xy_yb[L], A.C.v[0][1]);
@@ -523,9 +637,10 @@ struct ShellBoxes {
     int nbz[6], nby[6];  // blocks along z and y
     int start[7];        // prefix sums of the block counts
 };
-template <int SO, typename T, int ARITH>
+template <int SO, typename T, int ARITH, bool HET = false>
 __global__ void __launch_bounds__(OPESCI_FACE_THREADS)
-velocity_shell_kernel(FieldPtrs F, GridGeom G, StaggeredCoefs C, int t0, int t1, const __grid_constant__ ShellBoxes B)
+velocity_shell_kernel(FieldPtrs F, GridGeom G, StaggeredCoefs C, int t0, int t1, const __grid_constant__ ShellBoxes B,
+                      MediaPtrs MD, HeteroCoefs HC)
 {
     constexpr int M = SO / 2;
     int b = 0;
@@ -549,7 +664,28 @@ velocity_shell_kernel(FieldPtrs F, GridGeom G, StaggeredCoefs C, int t0, int t1,
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         T *Va = (T *)F.f[F_U + a];
-        if (ARITH == OPESCI_ARITH_REFERENCE) {
+        if constexpr (HET) {
+            const float b = MD.m[OPESCI_MEDIA_BETA1 + a][p];
+            if (ARITH == OPESCI_ARITH_REFERENCE) {
+                float acc = 0;
+                bool first = true;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const float *g = (const float *)F.f[opnd[a][d]] + w;
+                    if (d == a) window_ref_h<M, true, 1>(acc, first, g, st[d], HC.c[d], HC.c2[d], b, b);
+                    else window_ref_h<M, false, 1>(acc, first, g, st[d], HC.c[d], HC.c2[d], b, b);
+                }
+                Va[w] = __fadd_rn(acc, Va[r]);
+            } else {
+                float acc = 0;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const float *g = (const float *)F.f[opnd[a][d]] + w;
+                    acc += (d == a) ? window_fast<M, float, true>(g, st[d], HC.c[d]) : window_fast<M, float, false>(g, st[d], HC.c[d]);
+                }
+                Va[w] = Va[r] + b * acc;
+            }
+        } else if (ARITH == OPESCI_ARITH_REFERENCE) {
             T acc = 0;
             bool first = true;
 #pragma unroll

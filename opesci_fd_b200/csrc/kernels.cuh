@@ -407,14 +407,17 @@ face_batch(FieldPtrs F, GridGeom G, const __grid_constant__ FaceBatch B, MediaPt
         T acc = 0;
         double accd = 0.0;   // the running sum once a double-typed term (pow(mu,2)) has been met
         bool first = true, wide = false;
+        // heterogeneous Levander loops: every `/D` term of one equation shares D = da*lambda + db*mu
+        float D = 0.f;
+        if (L.eq.da != 0.f || L.eq.db != 0.f)
+            D = __fadd_rn(__fmul_rn(L.eq.da, MD.m[OPESCI_MEDIA_LAMBDA][p + L.eq.doff]),
+                          __fmul_rn(L.eq.db, MD.m[OPESCI_MEDIA_MU][p + L.eq.doff]));
         for (int k = 0; k < L.eq.nterm; ++k) {
             const DevTerm &t = L.eq.term[k];
             const T g = ((const T *)F.f[t.field])[lv[t.level] + p + t.off];
             T v = t.kind == TERM_MUL ? mul_rn<T>((T)t.coef, g) : g;
             if (t.mk != MK_NONE) {
                 // heterogeneous Levander terms: fp32 only, the reference's left-to-right evaluation
-                const float D = __fadd_rn(__fmul_rn(L.eq.da, MD.m[OPESCI_MEDIA_LAMBDA][p + L.eq.doff]),
-                                          __fmul_rn(L.eq.db, MD.m[OPESCI_MEDIA_MU][p + L.eq.doff]));
                 const float A = MD.m[t.ma][p + t.moffa], Bm = MD.m[t.mb][p + t.moffb];
                 if (t.mk == MK_SQ_DIV) {
                     double vd = __ddiv_rn(__dmul_rn((double)v, __dmul_rn((double)Bm, (double)Bm)), (double)D);

@@ -620,11 +620,12 @@ struct Stepper {
             using K = FusedCfg<M>;
             const Model &Md = R.M;
             FusedArgs A;
-            A.F = ptrs(); A.G = Md.G; A.C = Md.sc; A.t0 = t0; A.t1 = t1; A.xchunk = R.xchunk;
+            A.F = ptrs(); A.G = Md.G; A.C = Md.sc; A.MD = media(); A.HC = Md.hc; A.t0 = t0; A.t1 = t1; A.xchunk = R.xchunk;
             A.mode = mode;
             for (int k = 0; k < 3; ++k) { A.box_lo[k] = R.box_lo[k]; A.box_hi[k] = R.box_hi[k]; }
             dim3 grid((Md.G.dim[2] - 2 * M + K::CZ - 1) / K::CZ, (Md.G.dim[1] - 2 * M + K::CY - 1) / K::CY, R.nchunks);
-            fused_step<SO, ARITH><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
+            if (Md.p.hetero) fused_step<SO, ARITH, true><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
+            else fused_step<SO, ARITH, false><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
             check();
         }
     }
@@ -659,7 +660,10 @@ struct Stepper {
                 }
             B.start[6] = total;
             if (total == 0) return;
-            velocity_shell_kernel<SO, T, ARITH><<<total, OPESCI_FACE_THREADS, 0, st>>>(ptrs(), Md.G, Md.sc, t0, t1, B);
+            if (Md.p.hetero)
+                velocity_shell_kernel<SO, T, ARITH, true><<<total, OPESCI_FACE_THREADS, 0, st>>>(ptrs(), Md.G, Md.sc, t0, t1, B, media(), Md.hc);
+            else
+                velocity_shell_kernel<SO, T, ARITH, false><<<total, OPESCI_FACE_THREADS, 0, st>>>(ptrs(), Md.G, Md.sc, t0, t1, B, media(), Md.hc);
             check();
         }
     }
@@ -694,7 +698,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 template <int M, int ARITH> int set_fused_attr()
 {
-    CUDA_OK(cudaFuncSetAttribute(fused_step<2 * M, ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<M>::SMEM));
+    CUDA_OK(cudaFuncSetAttribute(fused_step<2 * M, ARITH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<M>::SMEM));
+    CUDA_OK(cudaFuncSetAttribute(fused_step<2 * M, ARITH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<M>::SMEM));
     return 0;
 }
 
@@ -704,7 +709,6 @@ int setup_fused(Run &R)
     const OpesciB200Params &p = M.p;
     R.fused = false;
     if (p.kind != OPESCI_KIND_STAGGERED_ELASTIC || p.is_double || p.so > 4 || (p.flags & OPESCI_FORCE_UNFUSED)) return 0;
-    if (p.hetero) return 0;   // heterogeneous media: two-pass kernels (hetero.cuh)
     for (int d = 0; d < 3; ++d)
         if (M.G.dim[d] < 6 * M.m + 4) return 0;   // no deep interior worth fusing
     static EncodeTiledFn encode = nullptr;
