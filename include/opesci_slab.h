@@ -10,6 +10,7 @@
  * travels at most 2m+3 planes inwards (stress update m, velocity update m, the Levander ghost
  * loops on the y/z faces chain through 3 more x-neighbours: SURVEY.md 8e), so H >= 2m+3 keeps every
  * owned plane exact: results are bit-identical to the single-domain run.
+ * The regular-grid acoustic model has no ghost-cell loops: an error travels m planes per step, H >= m.
  */
 #ifndef OPESCI_SLAB_H
 #define OPESCI_SLAB_H
@@ -23,8 +24,9 @@ typedef struct OpesciSlab {
     int lo_face, hi_face;
 } OpesciSlab;
 
-/* returns 0 on success, 1 if the slabs would be thinner than the halo */
-static inline int opesci_slab_make(OpesciSlab *s, int rank, int nranks, int gdim, int m, int halo)
+/* `need`: planes an error can travel inwards per step (2m+3 staggered elastic, m regular acoustic).
+ * returns 0 on success, 1 if the slabs would be thinner than the halo or the halo is too thin */
+static inline int opesci_slab_make(OpesciSlab *s, int rank, int nranks, int gdim, int m, int halo, int need)
 {
     if (nranks < 1) nranks = 1;
     const int n_int = gdim - 2 * m;
@@ -38,7 +40,7 @@ static inline int opesci_slab_make(OpesciSlab *s, int rank, int nranks, int gdim
     s->own_hi = s->hi_face ? gdim : s->X1;
     s->L0 = s->lo_face ? 0 : s->X0 - halo;
     s->L1 = s->hi_face ? gdim : s->X1 + halo;
-    if (nranks > 1 && (base < halo || halo < 2 * m + 3)) return 1;
+    if (nranks > 1 && (base < halo || halo < need)) return 1;
     return 0;
 }
 

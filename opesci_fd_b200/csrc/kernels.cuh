@@ -379,7 +379,8 @@ struct FaceBatch {
 #define OPESCI_FACE_THREADS 128
 template <typename T>
 __global__ void __launch_bounds__(OPESCI_FACE_THREADS)
-face_batch(FieldPtrs F, GridGeom G, const __grid_constant__ FaceBatch B, MediaPtrs MD)
+face_batch(const __grid_constant__ FieldPtrs F, const __grid_constant__ GridGeom G, const __grid_constant__ FaceBatch B,
+           const __grid_constant__ MediaPtrs MD)
 {
     int li = 0;
     for (int k = 1; k < B.count; ++k)
@@ -404,41 +405,64 @@ face_batch(FieldPtrs F, GridGeom G, const __grid_constant__ FaceBatch B, MediaPt
     } else {
         const long long p = q + (long long)L.n * G.s[d];
         const long long lv[2] = {(long long)L.lv0 * G.level, (long long)L.lv1 * G.level};
-        T acc = 0;
-        double accd = 0.0;   // the running sum once a double-typed term (pow(mu,2)) has been met
-        bool first = true, wide = false;
+        // Phase 1: issue every operand load of the sum before any arithmetic.  The sum itself is a serial
+        // chain (reference order); with the loads inside that chain every term would cost a full memory
+        // latency (measured: these loops were latency-bound at ~14 dependent loads per cell).
+        const int nt = L.eq.nterm;
+        const bool het = L.eq.da != 0.f || L.eq.db != 0.f || L.eq.term[nt - 1].mk != MK_NONE || L.eq.term[0].mk != MK_NONE;
+        T g[OPESCI_MAX_FACE_TERMS];
+        float ma[OPESCI_MAX_FACE_TERMS], mb[OPESCI_MAX_FACE_TERMS];
+#pragma unroll
+        for (int k = 0; k < OPESCI_MAX_FACE_TERMS; ++k) {
+            g[k] = 0;
+            ma[k] = mb[k] = 0.f;
+            if (k < nt) {
+                const DevTerm &t = L.eq.term[k];
+                g[k] = ((const T *)F.f[t.field])[lv[t.level] + p + t.off];
+                if (het && t.mk != MK_NONE) {
+                    ma[k] = MD.m[t.ma][p + t.moffa];
+                    mb[k] = MD.m[t.mb][p + t.moffb];
+                }
+            }
+        }
         // heterogeneous Levander loops: every `/D` term of one equation shares D = da*lambda + db*mu
         float D = 0.f;
         if (L.eq.da != 0.f || L.eq.db != 0.f)
             D = __fadd_rn(__fmul_rn(L.eq.da, MD.m[OPESCI_MEDIA_LAMBDA][p + L.eq.doff]),
                           __fmul_rn(L.eq.db, MD.m[OPESCI_MEDIA_MU][p + L.eq.doff]));
-        for (int k = 0; k < L.eq.nterm; ++k) {
-            const DevTerm &t = L.eq.term[k];
-            const T g = ((const T *)F.f[t.field])[lv[t.level] + p + t.off];
-            T v = t.kind == TERM_MUL ? mul_rn<T>((T)t.coef, g) : g;
-            if (t.mk != MK_NONE) {
-                // heterogeneous Levander terms: fp32 only, the reference's left-to-right evaluation
-                const float A = MD.m[t.ma][p + t.moffa], Bm = MD.m[t.mb][p + t.moffb];
+        // Phase 2: the emitted sum, term by term
+        T acc = 0;
+        double accd = 0.0;   // the running sum once a double-typed term (pow(mu,2)) has been met
+        bool first = true, wide = false;
+#pragma unroll
+        for (int k = 0; k < OPESCI_MAX_FACE_TERMS; ++k) {
+            if (k < nt) {
+                const DevTerm &t = L.eq.term[k];
+                T v = t.kind == TERM_MUL ? mul_rn<T>((T)t.coef, g[k]) : g[k];
                 if (t.mk == MK_SQ_DIV) {
-                    double vd = __ddiv_rn(__dmul_rn((double)v, __dmul_rn((double)Bm, (double)Bm)), (double)D);
+                    // `pow(mu,2)` is double in the emitted C++: the term, and from it on the running sum, are double
+                    double vd = __ddiv_rn(__dmul_rn((double)v, __dmul_rn((double)mb[k], (double)mb[k])), (double)D);
                     if (t.kind == TERM_MINUS) vd = -vd;
                     accd = first ? vd : __dadd_rn(wide ? accd : (double)acc, vd);
-                    first = false;
                     wide = true;
-                    continue;
+                } else {
+                    if (t.mk != MK_NONE) {
+                        // heterogeneous terms: fp32 only, the reference's left-to-right evaluation
+                        const float A = ma[k], Bm = mb[k];
+                        float w = (float)v;
+                        if (t.mk == MK_A) w = __fmul_rn(w, A);
+                        else if (t.mk == MK_A_DIV) w = __fdiv_rn(__fmul_rn(w, A), D);
+                        else if (t.mk == MK_AB_DIV) w = __fdiv_rn(__fmul_rn(__fmul_rn(w, A), Bm), D);
+                        else w = __fdiv_rn(__fmul_rn(w, A), Bm);
+                        v = (T)w;
+                    }
+                    if (t.kind == TERM_MINUS) v = -v;
+                    if (first) acc = v;
+                    else if (wide) accd = __dadd_rn(accd, (double)v);
+                    else acc = add_rn<T>(acc, v);
                 }
-                float w = (float)v;
-                if (t.mk == MK_A) w = __fmul_rn(w, A);
-                else if (t.mk == MK_A_DIV) w = __fdiv_rn(__fmul_rn(w, A), D);
-                else if (t.mk == MK_AB_DIV) w = __fdiv_rn(__fmul_rn(__fmul_rn(w, A), Bm), D);
-                else w = __fdiv_rn(__fmul_rn(w, A), Bm);
-                v = (T)w;
+                first = false;
             }
-            if (t.kind == TERM_MINUS) v = -v;
-            if (first) acc = v;
-            else if (wide) accd = __dadd_rn(accd, (double)v);
-            else acc = add_rn<T>(acc, v);
-            first = false;
         }
         ((T *)F.f[L.eq.out])[lv[L.eq.out_level] + p] = wide ? (T)accd : acc;
     }

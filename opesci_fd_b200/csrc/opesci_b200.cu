@@ -809,7 +809,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
         S.template stress_bc<T>(0, 0, true);   // initialise_bc (staggeredgrid.py:866-879)
         S.template velocity_bc<T>(0);
     } else {
-        S.template acoustic<SO, T, ARITH>(0, 0, 1, true);
+        S.template acoustic<SO, T, ARITH>(0, 0, 1, true);   // second initialisation: level 1 from level 0
     }
     const bool slabs = M.slab.nranks > 1;
     // halo refresh: all fields, one time level, H planes per inner side (contiguous blocks)
@@ -831,7 +831,8 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
         NCCL_OK(g_nccl.GroupEnd());
         return 0;
     };
-    if (slabs && exchange(0)) return 1;
+    // staggered: level 0 after the initial BC pass; regular: level 1 (level 0 is analytic on every stored plane)
+    if (slabs && exchange(staggered ? 0 : 1)) return 1;
     CUDA_OK(cudaStreamSynchronize(st));
     if (S.err != cudaSuccess) return fail("kernel launch failed during initialisation: %s", cudaGetErrorString(S.err));
 
@@ -936,7 +937,8 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
             } else {
                 if (staggered) S.template staggered_step<SO, T, ARITH>(ti);
                 else S.template acoustic_step<SO, T, ARITH>(ti);
-                if (slabs && exchange((ti + 1) % period)) return 1;   // level t1 of this step
+                // the level this step wrote: t1 = (ti+1)%2 (staggered), t2 = (ti+2)%3 (regular)
+                if (slabs && exchange(staggered ? (ti + 1) % 2 : (ti + 2) % 3)) return 1;
                 ++ti;
             }
         }
@@ -1234,14 +1236,13 @@ int opesci_b200_configure(const OpesciB200Params *params)
     if (params->so < 2 || params->so > 12 || (params->so & 1)) return fail("opesci_b200_configure: so must be even, 2..12");
     for (int d = 0; d < 3; ++d)
         if (params->dim[d] < 2 * (params->so / 2) + 1) return fail("opesci_b200_configure: grid too small for the stencil");
-    if (params->slab_nranks > 1 && params->kind != OPESCI_KIND_STAGGERED_ELASTIC)
-        return fail("opesci_b200_configure: slab decomposition is implemented for the staggered elastic model");
     Model &M = g_model;
     M = Model();
     M.p = *params;
     M.m = params->so / 2;
     const int nranks = params->slab_nranks > 1 ? params->slab_nranks : 1;
-    if (opesci_slab_make(&M.slab, nranks > 1 ? params->slab_rank : 0, nranks, params->dim[0], M.m, OPESCI_SLAB_HALO))
+    const int need = params->kind == OPESCI_KIND_REGULAR_ACOUSTIC ? M.m : 2 * M.m + 3;   // include/opesci_slab.h
+    if (opesci_slab_make(&M.slab, nranks > 1 ? params->slab_rank : 0, nranks, params->dim[0], M.m, OPESCI_SLAB_HALO, need))
         return fail("opesci_b200_configure: slabs thinner than the halo (or so > 4 with slabs): use fewer ranks");
     if (nranks > 1 && (!g_nccl.comm || g_nccl.nranks != nranks || g_nccl.rank != params->slab_rank))
         return fail("opesci_b200_configure: slab_nranks > 1 needs opesci_b200_comm_init with the same rank / size first");
@@ -1448,7 +1449,7 @@ int opesci_b200_comm_init(int rank, int nranks, const void *id_bytes, int nbytes
 int opesci_b200_slab_range(int rank, int nranks, int gdim1, int so, int *L0, int *L1)
 {
     OpesciSlab sl;
-    if (opesci_slab_make(&sl, rank, nranks, gdim1, so / 2, OPESCI_SLAB_HALO)) return fail("opesci_b200_slab_range: slabs thinner than the halo");
+    if (opesci_slab_make(&sl, rank, nranks, gdim1, so / 2, OPESCI_SLAB_HALO, 0)) return fail("opesci_b200_slab_range: slabs thinner than the halo");
     if (L0) *L0 = sl.L0;
     if (L1) *L1 = sl.L1;
     return 0;

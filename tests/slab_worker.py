@@ -91,7 +91,7 @@ def main():
     n = p.nlevels * (L1 - L0) * p.dim[1] * p.dim[2]
     ctype = ctypes.c_double if p.is_double else ctypes.c_float
     fields = []
-    for k in range(9):
+    for k in range(p.nfields):
         buf = ctypes.cast(grid._arg_grid.field[k], ctypes.POINTER(ctype * n)).contents
         fields.append(np.frombuffer(buf, dtype=np.float64 if p.is_double else np.float32).reshape(
             p.nlevels, L1 - L0, p.dim[1], p.dim[2]).copy())
