@@ -126,6 +126,7 @@ enum {
     OPESCI_HOST_MIRROR_MASK = 0x30,
     OPESCI_NO_CUDA_GRAPH = 1 << 8,
     OPESCI_FORCE_UNFUSED = 1 << 9,      /* two-pass stress / velocity kernels (diagnostic) */
+    OPESCI_FORCE_TILED = 1 << 11,       /* TMA-tiled two-pass kernels also where the fused kernel applies (diagnostic) */
     OPESCI_OVERLAP = 1 << 10            /* experimental: run the ghost loops of step n-1 concurrently with the tiles of
                                          * step n that cannot see them (bit-identical; no gain measured on B200) */
 };

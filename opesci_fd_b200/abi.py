@@ -29,6 +29,7 @@ HOST_MIRROR_NONE = 1 << 4
 NO_CUDA_GRAPH = 1 << 8
 FORCE_UNFUSED = 1 << 9
 OVERLAP = 1 << 10
+FORCE_TILED = 1 << 11
 
 FS_NONE, FS_LEVANDER, FS_ROBERTSSON = 0, 1, 2
 

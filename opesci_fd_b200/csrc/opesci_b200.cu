@@ -26,6 +26,7 @@
 #include "fused.cuh"
 #include "hetero.cuh"
 #include "kernels.cuh"
+#include "tiled.cuh"
 
 using namespace opesci;
 
@@ -129,6 +130,8 @@ struct Run {
     size_t host_bytes_per_field = 0;
     bool fused = false;             // fused stress+velocity kernel in use
     CUtensorMap tmap[3];            // U, V, W (both time levels; level selected through the x coordinate)
+    bool tiled = false;             // TMA-tiled two-pass kernels in use (tiled.cuh: so >= 6, fp64)
+    CUtensorMap tmap9[OPESCI_MAX_FIELDS];   // all nine fields, box = TileCfg tile
     int xchunk = 0, nchunks = 1;
     bool overlap = false;           // ghost loops of step n-1 run concurrently with the independent tiles of step n
     int box_lo[3] = {0, 0, 0}, box_hi[3] = {0, 0, 0};   // independent tiles (tile_y, tile_z, chunk)
@@ -383,8 +386,53 @@ struct Stepper {
         return dim3((nz + blk.x - 1) / blk.x, (ny + blk.y - 1) / blk.y, nx);
     }
 
+    // TMA-tiled two-pass kernels (tiled.cuh)
+    template <int SO, typename T> dim3 tiled_grid(int *xchunk) const
+    {
+        using K = TileCfg<SO / 2, T>;
+        const Model &M = R.M;
+        const int nx = M.G.dim[0] - 2 * M.m, ny = M.G.dim[1] - 2 * M.m, nz = M.G.dim[2] - 2 * M.m;
+        const int nbz = (nz + K::TZ - 1) / K::TZ, nby = (ny + K::TY - 1) / K::TY;
+        int nchunks = (8 * 148 + nbz * nby - 1) / (nbz * nby);       // >= 8 CTAs per SM over the launch
+        const int maxc = nx / (16 * M.m) > 0 ? nx / (16 * M.m) : 1;   // keep the 2m-plane warm-up of a chunk small
+        if (nchunks > maxc) nchunks = maxc;
+        if (nchunks < 1) nchunks = 1;
+        *xchunk = (nx + nchunks - 1) / nchunks;
+        return dim3(nbz, nby, (nx + *xchunk - 1) / *xchunk);
+    }
+    template <int SO, typename T, int ARITH> void stress_tiled_launch(int t0, int t1)
+    {
+        using K = TileCfg<SO / 2, T>;
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(stress_tiled<SO, T, ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::smem(3));
+            attr = true;
+        }
+        TileArgs A;
+        A.F = ptrs(); A.G = R.M.G; A.C = R.M.sc; A.t0 = t0; A.t1 = t1;
+        const dim3 grid = tiled_grid<SO, T>(&A.xchunk);
+        stress_tiled<SO, T, ARITH><<<grid, K::THREADS, K::smem(3), st>>>(R.tmap9[F_U], R.tmap9[F_V], R.tmap9[F_W], A);
+        check();
+    }
+    template <int SO, typename T, int ARITH> void velocity_tiled_launch(int t0, int t1)
+    {
+        using K = TileCfg<SO / 2, T>;
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(velocity_tiled<SO, T, ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::smem(5));
+            attr = true;
+        }
+        TileArgs A;
+        A.F = ptrs(); A.G = R.M.G; A.C = R.M.sc; A.t0 = t0; A.t1 = t1;
+        const dim3 grid = tiled_grid<SO, T>(&A.xchunk);
+        velocity_tiled<SO, T, ARITH><<<grid, K::THREADS, K::smem(5), st>>>(R.tmap9[F_TXY], R.tmap9[F_TYY], R.tmap9[F_TYZ], R.tmap9[F_TXZ],
+                                                                             R.tmap9[F_TZZ], A);
+        check();
+    }
+
     template <int SO, typename T, int ARITH> void stress(int t0, int t1)
     {
+        if (R.tiled) { stress_tiled_launch<SO, T, ARITH>(t0, t1); return; }
         dim3 blk(64, 4);
         if constexpr (sizeof(T) == 4) {
             if (R.M.p.hetero) {
@@ -398,6 +446,7 @@ struct Stepper {
     }
     template <int SO, typename T, int ARITH> void velocity(int t0, int t1)
     {
+        if (R.tiled) { velocity_tiled_launch<SO, T, ARITH>(t0, t1); return; }
         dim3 blk(64, 4);
         if constexpr (sizeof(T) == 4) {
             if (R.M.p.hetero) {
@@ -703,22 +752,53 @@ template <int M, int ARITH> int set_fused_attr()
     return 0;
 }
 
+EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return nullptr;
+        encode = (EncodeTiledFn)fn;
+    }
+    return encode;
+}
+
+// TMA-tiled two-pass kernels (tiled.cuh) for the staggered configurations the fused kernel does not cover
+int setup_tiled(Run &R)
+{
+    const Model &M = R.M;
+    const OpesciB200Params &p = M.p;
+    R.tiled = false;
+    if (p.kind != OPESCI_KIND_STAGGERED_ELASTIC || R.fused || p.hetero || (p.flags & OPESCI_FORCE_UNFUSED)) return 0;
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return fail("cuTensorMapEncodeTiled not available from the driver");
+    const int esz = p.is_double ? 8 : 4, al = 16 / esz;
+    const int VY = 8 + 2 * M.m, VZ = (32 + 2 * M.m + al - 1) / al * al;   // TileCfg<M,T>
+    for (int f = 0; f < 9; ++f) {
+        cuuint64_t gdim[3] = {(cuuint64_t)p.dim[2], (cuuint64_t)p.dim[1], (cuuint64_t)M.G.dim[0] * p.nlevels};
+        cuuint64_t gstride[2] = {(cuuint64_t)M.G.s[1] * esz, (cuuint64_t)M.G.s[0] * esz};
+        cuuint32_t box[3] = {(cuuint32_t)VZ, (cuuint32_t)VY, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult rc = encode(&R.tmap9[f], p.is_double ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, R.dev[f],
+                             gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (tiled two-pass kernels)");
+    }
+    R.tiled = true;
+    return 0;
+}
+
 int setup_fused(Run &R)
 {
     const Model &M = R.M;
     const OpesciB200Params &p = M.p;
     R.fused = false;
-    if (p.kind != OPESCI_KIND_STAGGERED_ELASTIC || p.is_double || p.so > 4 || (p.flags & OPESCI_FORCE_UNFUSED)) return 0;
+    if (p.kind != OPESCI_KIND_STAGGERED_ELASTIC || p.is_double || p.so > 4 || (p.flags & (OPESCI_FORCE_UNFUSED | OPESCI_FORCE_TILED))) return 0;
     for (int d = 0; d < 3; ++d)
         if (M.G.dim[d] < 6 * M.m + 4) return 0;   // no deep interior worth fusing
-    static EncodeTiledFn encode = nullptr;
-    if (!encode) {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
-            return fail("cuTensorMapEncodeTiled not available from the driver");
-        encode = (EncodeTiledFn)fn;
-    }
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return fail("cuTensorMapEncodeTiled not available from the driver");
     const int m = M.m;
     const int VZ = m == 1 ? FusedCfg<1>::VZ : FusedCfg<2>::VZ, VY = 16 + 2 * m;
     for (int f = 0; f < 3; ++f) {
@@ -1334,6 +1414,7 @@ int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
     if (setup_media(*R, st)) return bail(1);
     if (upload_programs(*R)) return bail(1);
     if (setup_fused(*R)) return bail(1);
+    if (setup_tiled(*R)) return bail(1);
     double secs = 0.0;
     if (dispatch(*R, st, &secs)) return bail(1);
     g_loop_seconds = secs;

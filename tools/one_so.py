@@ -7,5 +7,7 @@ from opesci_fd_b200 import abi  # noqa: E402
 if __name__ == "__main__":
     n, so = int(sys.argv[1]), int(sys.argv[2])
     double = len(sys.argv) > 3 and sys.argv[3] == "f64"
-    extra = abi.FORCE_UNFUSED if (len(sys.argv) > 4 and sys.argv[4] == "v1") else 0
-    run("eigenwave3d", n, so, 4, double, abi.ARITH_FAST, abi.load_library(), extra)
+    mode = sys.argv[4] if len(sys.argv) > 4 else ""
+    extra = {"v1": abi.FORCE_UNFUSED, "tiled": abi.FORCE_TILED}.get(mode, 0)
+    steps = int(sys.argv[5]) if len(sys.argv) > 5 else 4
+    run("eigenwave3d", n, so, steps, double, abi.ARITH_FAST, abi.load_library(), extra)
