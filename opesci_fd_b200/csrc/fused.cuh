@@ -122,7 +122,13 @@ __device__ __forceinline__ void window_ref_arr_h(float &acc, bool &first, const 
 }
 
 template <int M> struct FusedCfg {
-    static constexpr int EZ = 64, EY = 16;                 // threads = stress tile (incl. recomputed halo)
+#ifndef OPESCI_FUSED_EZ
+#define OPESCI_FUSED_EZ 64
+#endif
+#ifndef OPESCI_FUSED_MINB
+#define OPESCI_FUSED_MINB 1
+#endif
+    static constexpr int EZ = OPESCI_FUSED_EZ, EY = 16;     // threads = stress tile (incl. recomputed halo)
     // stored tile.  TMA needs the innermost box coordinate 16-B aligned (measured on B200: an
     // unaligned start raises "illegal instruction"), so tiles advance in multiples of 4 floats
     // along z and the box starts OFFZ >= M floats left of the stress tile.
@@ -144,7 +150,9 @@ struct FusedArgs {
     MediaPtrs MD;     // heterogeneous mode (HET kernels): per-cell media, +32 B/point of read traffic
     HeteroCoefs HC;
     int t0, t1;
-    int xchunk;       // planes per x-chunk
+#define OPESCI_MAX_CHUNKS 20
+    int xs[OPESCI_MAX_CHUNKS + 1];   // x-chunk c covers planes [xs[c], xs[c+1]); blockIdx.z + chunk0 selects the chunk
+    int chunk0;
     // Tile subset of this launch.  The tiles inside the box [box_lo, box_hi) (tile_y, tile_z, chunk)
     // neither read nor write any cell the ghost-cell loops / shell update of the PREVIOUS step touch,
     // so they can run concurrently with those loops; the remaining tiles run afterwards.
@@ -199,7 +207,7 @@ __device__ __forceinline__ void gstore2(float *p, float a, float b)
 // 8-byte loads, which halves the load/store-unit instruction count (the busiest pipe of the
 // one-point-per-thread version, ncu: profiles/r01_fused_v2_ncu_summary.txt).
 template <int SO, int ARITH, bool HET = false>
-__global__ void __launch_bounds__(FusedCfg<SO / 2>::THREADS, 1)
+__global__ void __launch_bounds__(FusedCfg<SO / 2>::THREADS, OPESCI_FUSED_MINB)
 fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
            const __grid_constant__ CUtensorMap tmW, const FusedArgs A)
 {
@@ -220,13 +228,14 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     const int tid = threadIdx.x;
     if (A.mode != 0) {
         const bool inside = (int)blockIdx.y >= A.box_lo[0] && (int)blockIdx.y < A.box_hi[0] && (int)blockIdx.x >= A.box_lo[1] &&
-                            (int)blockIdx.x < A.box_hi[1] && (int)blockIdx.z >= A.box_lo[2] && (int)blockIdx.z < A.box_hi[2];
+                            (int)blockIdx.x < A.box_hi[1] && (int)blockIdx.z + A.chunk0 >= A.box_lo[2] && (int)blockIdx.z + A.chunk0 < A.box_hi[2];
         if ((A.mode == 1) != inside) return;
     }
     const int tz = 2 * (tid % (K::EZ / 2)), ty = tid / (K::EZ / 2);          // lane 0 sits at tz, lane 1 at tz+1
     const int ye = blockIdx.y * K::CY + ty, ze = blockIdx.x * K::CZ + tz;   // global coords of lane 0
-    const int xa = M + blockIdx.z * A.xchunk;
-    const int xb = min(xa + A.xchunk, G.dim[0] - M);
+    const int chunk = blockIdx.z + A.chunk0;
+    const int xa = A.xs[chunk];
+    const int xb = A.xs[chunk + 1];
     const int xs_begin = max(M, xa - M), xs_end = min(G.dim[0] - M, xb + M);
     // plane p of U lives in slot (p - pbaseU) % RD, of V/W in slot (p - pbaseVW) % RD; with the
     // x loop unrolled RD times every slot index below is a compile-time constant

@@ -132,7 +132,9 @@ struct Run {
     CUtensorMap tmap[3];            // U, V, W (both time levels; level selected through the x coordinate)
     bool tiled = false;             // TMA-tiled two-pass kernels in use (tiled.cuh: so >= 6, fp64)
     CUtensorMap tmap9[OPESCI_MAX_FIELDS];   // all nine fields, box = TileCfg tile
-    int xchunk = 0, nchunks = 1;
+    int nchunks = 1;                // x-chunks of the fused kernel: chunk c covers planes [xs[c], xs[c+1])
+    int xs[OPESCI_MAX_CHUNKS + 1] = {};
+    int mid0 = 0, mid1 = 0;         // slabs: chunks [mid0, mid1) read no halo plane (they overlap the halo exchange)
     bool overlap = false;           // ghost loops of step n-1 run concurrently with the independent tiles of step n
     int box_lo[3] = {0, 0, 0}, box_hi[3] = {0, 0, 0};   // independent tiles (tile_y, tile_z, chunk)
 };
@@ -662,17 +664,21 @@ struct Stepper {
     }
 
     // fused stress+velocity launch (fused.cuh); only instantiated for so <= 4, fp32
-    template <int SO, typename T, int ARITH> void fused(int t0, int t1, int mode = 0)
+    template <int SO, typename T, int ARITH> void fused(int t0, int t1, int mode = 0, int chunk0 = 0, int count = -1)
     {
         if constexpr (SO <= 4 && sizeof(T) == 4) {
             constexpr int M = SO / 2;
             using K = FusedCfg<M>;
             const Model &Md = R.M;
             FusedArgs A;
-            A.F = ptrs(); A.G = Md.G; A.C = Md.sc; A.MD = media(); A.HC = Md.hc; A.t0 = t0; A.t1 = t1; A.xchunk = R.xchunk;
+            A.F = ptrs(); A.G = Md.G; A.C = Md.sc; A.MD = media(); A.HC = Md.hc; A.t0 = t0; A.t1 = t1;
+            for (int c = 0; c <= OPESCI_MAX_CHUNKS; ++c) A.xs[c] = R.xs[c];
+            A.chunk0 = chunk0;
+            if (count < 0) count = R.nchunks - chunk0;
+            if (count <= 0) return;
             A.mode = mode;
             for (int k = 0; k < 3; ++k) { A.box_lo[k] = R.box_lo[k]; A.box_hi[k] = R.box_hi[k]; }
-            dim3 grid((Md.G.dim[2] - 2 * M + K::CZ - 1) / K::CZ, (Md.G.dim[1] - 2 * M + K::CY - 1) / K::CY, R.nchunks);
+            dim3 grid((Md.G.dim[2] - 2 * M + K::CZ - 1) / K::CZ, (Md.G.dim[1] - 2 * M + K::CY - 1) / K::CY, count);
             if (Md.p.hetero) fused_step<SO, ARITH, true><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
             else fused_step<SO, ARITH, false><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
             check();
@@ -826,7 +832,31 @@ int setup_fused(Run &R)
         if (len < 8 * m && nc > 1) break;
         const double waves = (double)tiles * nc / nsm;
         const double eff = waves / (double)((long long)(waves + 0.999999)) * len / (len + 2.0 * m + 2.0);
-        if (eff > best) { best = eff; R.nchunks = nc; R.xchunk = len; }
+        if (eff > best) { best = eff; R.nchunks = nc; }
+    }
+    auto uniform = [&](int lo, int hi, int nc, int first) {   // chunks first .. first+nc-1 cover [lo, hi)
+        const int len = (hi - lo + nc - 1) / nc;
+        for (int c = 0; c <= nc; ++c) R.xs[first + c] = lo + c * len < hi ? lo + c * len : hi;
+    };
+    uniform(m, M.G.dim[0] - m, R.nchunks, 0);
+    R.mid0 = 0; R.mid1 = 0;
+    if (M.slab.nranks > 1) {
+        // Slabs: the fused kernel at plane x reads planes x-2m .. x+2m-1 (+1).  Thin end chunks hold every plane whose
+        // computation reads a halo plane; the chunks in between can run while the halo exchange of the previous step
+        // is still in flight (run_model).
+        const int E = M.slab.halo + 2 * m;                       // first / last plane index bound of the middle part
+        const int lo = M.slab.lo_face ? m : E, hi = M.slab.hi_face ? M.G.dim[0] - m : M.G.dim[0] - E;
+        if (hi - lo >= 8 * m) {
+            int c = 0;
+            if (!M.slab.lo_face) { R.xs[0] = m; R.xs[1] = lo; c = 1; }
+            R.mid0 = c;
+            const int nmid = R.nchunks < OPESCI_MAX_CHUNKS - 2 ? R.nchunks : OPESCI_MAX_CHUNKS - 2;
+            uniform(lo, hi, nmid, c);
+            c += nmid;
+            R.mid1 = c;
+            if (!M.slab.hi_face) { R.xs[c + 1] = M.G.dim[0] - m; ++c; }
+            R.nchunks = c;
+        }
     }
     // (opt-in, OPESCI_OVERLAP: measured no gain on B200 -- a resident fused CTA pins the SM's L1/shared split at
     // 228 KB shared, and the ghost kernels either cannot co-reside (default carve-out) or lose the L1 they live on)
@@ -838,8 +868,8 @@ int setup_fused(Run &R)
     if (M.slab.nranks == 1 && (p.flags & OPESCI_OVERLAP) && nx >= 6 * 48) {
         const int nc = nx >= 8 * 96 ? 8 : 6;
         R.nchunks = nc;
-        R.xchunk = (nx + nc - 1) / nc;
-        const int EY = 16, EZ = 64;
+        uniform(m, M.G.dim[0] - m, nc, 0);
+        const int EY = 16, EZ = OPESCI_FUSED_EZ;
         const int dims[3] = {M.G.dim[1], M.G.dim[2], M.G.dim[0]};
         const int ntile[3] = {(p.dim[1] - 2 * m + CY - 1) / CY, (p.dim[2] - 2 * m + CZ - 1) / CZ, nc};
         for (int a = 0; a < 3; ++a) {
@@ -849,9 +879,7 @@ int setup_fused(Run &R)
                 if (a == 0) { rlo = k * CY - m; rhi = k * CY + EY + m; }
                 else if (a == 1) { rlo = k * CZ - m; rhi = k * CZ + EZ + m; }
                 else {
-                    const int xa = m + k * R.xchunk;
-                    int xb = xa + R.xchunk;
-                    if (xb > dims[2] - m) xb = dims[2] - m;
+                    const int xa = R.xs[k], xb = R.xs[k + 1];
                     rlo = xa - 2 * m; rhi = xb + 2 * m + 1;
                 }
                 if (rlo >= 2 * m + 1 && rhi <= dims[a] - 2 * m - 1) { if (k < lo) lo = k; if (k + 1 > hi) hi = k + 1; }
@@ -893,7 +921,8 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     }
     const bool slabs = M.slab.nranks > 1;
     // halo refresh: all fields, one time level, H planes per inner side (contiguous blocks)
-    auto exchange = [&](int level) -> int {
+    auto exchange = [&](int level, cudaStream_t xs_) -> int {
+        cudaStream_t st = xs_;
         const OpesciSlab &sl = M.slab;
         const size_t plane = (size_t)M.G.s[0], nel = (size_t)sl.halo * plane;
         NCCL_OK(g_nccl.GroupStart());
@@ -912,7 +941,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
         return 0;
     };
     // staggered: level 0 after the initial BC pass; regular: level 1 (level 0 is analytic on every stored plane)
-    if (slabs && exchange(staggered ? 0 : 1)) return 1;
+    if (slabs && exchange(staggered ? 0 : 1, st)) return 1;
     CUDA_OK(cudaStreamSynchronize(st));
     if (S.err != cudaSuccess) return fail("kernel launch failed during initialisation: %s", cudaGetErrorString(S.err));
 
@@ -992,6 +1021,47 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
         CUDA_OK(cudaStreamSynchronize(st2));
         S.launches += SB.launches + graph_launches;
         if (SB.err != cudaSuccess && S.err == cudaSuccess) S.err = SB.err;
+    } else if (slabs && staggered && R.fused && R.mid1 > R.mid0) {
+        // ---- slabs, fused kernel: the halo exchange of step n (NCCL, own high-priority stream) runs while the middle
+        // x-chunks of step n+1 -- which read no halo plane -- are computed; the thin end chunks, the ghost loops and
+        // the shell follow once the exchange has landed.  Same kernels, same per-cell order as the serial schedule.
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_OK(cudaStreamCreateWithPriority(&st2, cudaStreamNonBlocking, prio_hi));
+        CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));   // step done on st -> exchange may start
+        CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));   // exchange done -> halo planes valid
+        bool pending = false;
+        auto step = [&](int ti) -> int {
+            const int t0 = ti % 2, t1 = (t0 + 1) % 2;
+            S.template fused<SO, T, ARITH>(t0, t1, 0, R.mid0, R.mid1 - R.mid0);
+            if (pending) { CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0)); pending = false; }
+            S.template fused<SO, T, ARITH>(t0, t1, 0, 0, R.mid0);
+            S.template fused<SO, T, ARITH>(t0, t1, 0, R.mid1, R.nchunks - R.mid1);
+            S.template stress_bc<T>(t0, t1, false);
+            S.template velocity_shell<SO, T, ARITH>(t0, t1);
+            S.template velocity_bc<T>(t1);
+            CUDA_OK(cudaEventRecord(ev_fork, st));
+            CUDA_OK(cudaStreamWaitEvent(st2, ev_fork, 0));
+            if (exchange(t1, st2)) return 1;
+            CUDA_OK(cudaEventRecord(ev_join, st2));
+            pending = true;
+            return 0;
+        };
+        auto drain = [&]() -> int {
+            if (pending) { CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0)); pending = false; }
+            return 0;
+        };
+        for (int ti = 0; ti < warm; ++ti)
+            if (step(ti)) return 1;
+        if (drain()) return 1;
+        S.launches = 0;
+        CUDA_OK(cudaEventRecord(e0, st));
+        for (int ti = warm; ti < nsteps; ++ti)
+            if (step(ti)) return 1;
+        if (drain()) return 1;
+        CUDA_OK(cudaEventRecord(e1, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        CUDA_OK(cudaStreamSynchronize(st2));
     } else {
     const bool use_graph = !(p.flags & OPESCI_NO_CUDA_GRAPH) && nsteps >= 2 * period && !slabs;
     if (use_graph) {
@@ -1018,7 +1088,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
                 if (staggered) S.template staggered_step<SO, T, ARITH>(ti);
                 else S.template acoustic_step<SO, T, ARITH>(ti);
                 // the level this step wrote: t1 = (ti+1)%2 (staggered), t2 = (ti+2)%3 (regular)
-                if (slabs && exchange(staggered ? (ti + 1) % 2 : (ti + 2) % 3)) return 1;
+                if (slabs && exchange(staggered ? (ti + 1) % 2 : (ti + 2) % 3, st)) return 1;
                 ++ti;
             }
         }
