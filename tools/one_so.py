@@ -10,4 +10,4 @@ if __name__ == "__main__":
     mode = sys.argv[4] if len(sys.argv) > 4 else ""
     extra = {"v1": abi.FORCE_UNFUSED, "tiled": abi.FORCE_TILED}.get(mode, 0)
     steps = int(sys.argv[5]) if len(sys.argv) > 5 else 4
-    run("eigenwave3d", n, so, steps, double, abi.ARITH_FAST, abi.load_library(), extra)
+    run("eigenwave3d", n, so, steps, double, abi.ARITH_FAST, abi.load_library(os.environ.get('OPESCI_LIB')), extra)
