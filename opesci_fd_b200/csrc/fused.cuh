@@ -340,6 +340,18 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
         for (int r = 0; r < RD; ++r) {
             const int xs = xs0 + r;
             if (xs >= xs_end) break;
+            // heterogeneous mode: lambda, mu, mu12, mu23, mu13 of the two cells (plane xs), issued before the waits so
+            // that their latency overlaps the TMA wait and the operand gather
+            T med[2][5];
+            if (HET) {
+                const int ids[5] = {OPESCI_MEDIA_LAMBDA, OPESCI_MEDIA_MU, OPESCI_MEDIA_MU12, OPESCI_MEDIA_MU23, OPESCI_MEDIA_MU13};
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const float *mp = A.MD.m[ids[k]] + pyz + px;
+                    if (inb2) { const float2 v = *reinterpret_cast<const float2 *>(mp); med[0][k] = v.x; med[1][k] = v.y; }
+                    else { med[0][k] = inb[0] ? mp[0] : 0.f; med[1][k] = inb[1] ? mp[1] : 0.f; }
+                }
+            }
             // ---- the newest planes of this iteration: relative plane index RD*q + r + 2M-1
             {
                 const int slot = (r + 2 * M - 1) % RD;
@@ -379,17 +391,6 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             load6(pv, fv);
             load6(pw, fw);
             T tn[2][6], uself[2], vself_next[2], wself_next[2];
-            // heterogeneous mode: lambda, mu, mu12, mu23, mu13 of the two cells (plane xs)
-            T med[2][5];
-            if (HET) {
-                const int ids[5] = {OPESCI_MEDIA_LAMBDA, OPESCI_MEDIA_MU, OPESCI_MEDIA_MU12, OPESCI_MEDIA_MU23, OPESCI_MEDIA_MU13};
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const float *mp = A.MD.m[ids[k]] + pyz + px;
-                    if (inb2) { const float2 v = *reinterpret_cast<const float2 *>(mp); med[0][k] = v.x; med[1][k] = v.y; }
-                    else { med[0][k] = inb[0] ? mp[0] : 0.f; med[1][k] = inb[1] ? mp[1] : 0.f; }
-                }
-            }
 #pragma unroll
             for (int L = 0; L < 2; ++L) {
                 T wz_b[2 * M], uz_f[2 * M], vz_f[2 * M];
@@ -517,6 +518,17 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                 *reinterpret_cast<float2 *>(s + 3 * K::SR * ST) = make_float2(tn[0][4], tn[1][4]);   // Tyz
                 *reinterpret_cast<float2 *>(s + 4 * K::SR * ST) = make_float2(tn[0][2], tn[1][2]);   // Tzz
             }
+            T bet[2][3];   // heterogeneous mode: beta1, beta2, beta3 of the two cells (plane xv = xs - M), issued before the barrier
+            if (HET) {
+                const bool vel_here = (vf_yz[0] || vf_yz[1]) && xs - M >= xv_lo && xs - M < xv_hi;
+                const long long pxv_ = px - (long long)(M + 1) * sx;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float2 v = make_float2(0.f, 0.f);
+                    if (vel_here) v = *reinterpret_cast<const float2 *>(A.MD.m[OPESCI_MEDIA_BETA1 + k] + pyz + pxv_);
+                    bet[0][k] = v.x; bet[1][k] = v.y;
+                }
+            }
             __syncthreads();
             // ---- the oldest planes (window entry 0, slot r) are dead: refill their slots
             if (tid == 0) {
@@ -553,15 +565,6 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                 load6(syz, fyz);
                 load6(szz, fzz);
                 T vout[2][3];
-                T bet[2][3];   // heterogeneous mode: beta1, beta2, beta3 of the two cells (plane xv)
-                if (HET) {
-                    const long long pxv_ = px - (long long)(M + 1) * sx;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const float2 v = *reinterpret_cast<const float2 *>(A.MD.m[OPESCI_MEDIA_BETA1 + k] + pyz + pxv_);
-                        bet[0][k] = v.x; bet[1][k] = v.y;
-                    }
-                }
 #pragma unroll
                 for (int L = 0; L < 2; ++L) {
                     T xz_zb[2 * M], yz_zb[2 * M], zz_zf[2 * M];

@@ -158,3 +158,19 @@ def synthetic_media(dims, seed=20261017):
     vp = (1.0 + 0.5 * gen.random(n, dtype=np.float32)).astype(np.float32).reshape(dims)
     vs = (0.4 + 0.3 * gen.random(n, dtype=np.float32)).astype(np.float32).reshape(dims)
     return rho, vp, vs
+
+
+def synthetic_media_planes(dims, plane0, nplanes, seed=20261017):
+    """The same kind of medium as `synthetic_media`, generated plane by plane from a counter-based key
+    (Philox keyed with (seed, global plane index)), so that every rank of a slab run can produce exactly
+    the planes it stores -- halo planes included -- without materialising the global arrays.
+    Returns rho, vp, vs of shape [nplanes][dim2][dim3] holding the global planes [plane0, plane0+nplanes)."""
+    import numpy as np
+    d2, d3 = int(dims[1]), int(dims[2])
+    out = [np.empty((nplanes, d2, d3), dtype=np.float32) for _ in range(3)]
+    for k in range(nplanes):
+        gen = np.random.Generator(np.random.Philox(key=[seed, plane0 + k]))
+        out[0][k] = (1.0 + 0.5 * gen.random((d2, d3), dtype=np.float32))
+        out[1][k] = (1.0 + 0.5 * gen.random((d2, d3), dtype=np.float32))
+        out[2][k] = (0.4 + 0.3 * gen.random((d2, d3), dtype=np.float32))
+    return tuple(out)
