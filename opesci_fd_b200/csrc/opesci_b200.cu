@@ -411,8 +411,20 @@ struct Stepper {
             attr = true;
         }
         TileArgs A;
-        A.F = ptrs(); A.G = R.M.G; A.C = R.M.sc; A.t0 = t0; A.t1 = t1;
+        A.F = ptrs(); A.G = R.M.G; A.C = R.M.sc; A.MD = media(); A.HC = R.M.hc; A.t0 = t0; A.t1 = t1;
         const dim3 grid = tiled_grid<SO, T>(&A.xchunk);
+        if constexpr (sizeof(T) == 4) {
+            if (R.M.p.hetero) {
+                static bool attr_h = false;
+                if (!attr_h) {
+                    cudaFuncSetAttribute(stress_tiled<SO, T, ARITH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::smem(3));
+                    attr_h = true;
+                }
+                stress_tiled<SO, T, ARITH, true><<<grid, K::THREADS, K::smem(3), st>>>(R.tmap9[F_U], R.tmap9[F_V], R.tmap9[F_W], A);
+                check();
+                return;
+            }
+        }
         stress_tiled<SO, T, ARITH><<<grid, K::THREADS, K::smem(3), st>>>(R.tmap9[F_U], R.tmap9[F_V], R.tmap9[F_W], A);
         check();
     }
@@ -425,8 +437,21 @@ struct Stepper {
             attr = true;
         }
         TileArgs A;
-        A.F = ptrs(); A.G = R.M.G; A.C = R.M.sc; A.t0 = t0; A.t1 = t1;
+        A.F = ptrs(); A.G = R.M.G; A.C = R.M.sc; A.MD = media(); A.HC = R.M.hc; A.t0 = t0; A.t1 = t1;
         const dim3 grid = tiled_grid<SO, T>(&A.xchunk);
+        if constexpr (sizeof(T) == 4) {
+            if (R.M.p.hetero) {
+                static bool attr_h = false;
+                if (!attr_h) {
+                    cudaFuncSetAttribute(velocity_tiled<SO, T, ARITH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::smem(5));
+                    attr_h = true;
+                }
+                velocity_tiled<SO, T, ARITH, true><<<grid, K::THREADS, K::smem(5), st>>>(R.tmap9[F_TXY], R.tmap9[F_TYY], R.tmap9[F_TYZ],
+                                                                                         R.tmap9[F_TXZ], R.tmap9[F_TZZ], A);
+                check();
+                return;
+            }
+        }
         velocity_tiled<SO, T, ARITH><<<grid, K::THREADS, K::smem(5), st>>>(R.tmap9[F_TXY], R.tmap9[F_TYY], R.tmap9[F_TYZ], R.tmap9[F_TXZ],
                                                                              R.tmap9[F_TZZ], A);
         check();
@@ -776,7 +801,7 @@ int setup_tiled(Run &R)
     const Model &M = R.M;
     const OpesciB200Params &p = M.p;
     R.tiled = false;
-    if (p.kind != OPESCI_KIND_STAGGERED_ELASTIC || R.fused || p.hetero || (p.flags & OPESCI_FORCE_UNFUSED)) return 0;
+    if (p.kind != OPESCI_KIND_STAGGERED_ELASTIC || R.fused || (p.flags & OPESCI_FORCE_UNFUSED)) return 0;
     EncodeTiledFn encode = get_encode();
     if (!encode) return fail("cuTensorMapEncodeTiled not available from the driver");
     const int esz = p.is_double ? 8 : 4, al = 16 / esz;

@@ -17,6 +17,7 @@
 // asynchronous.  Reference arithmetic: same term order and roundings as the emitted code (window_ref_arr).
 #pragma once
 #include "fused.cuh"
+#include "hetero.cuh"
 #include "kernels.cuh"
 
 namespace opesci {
@@ -36,12 +37,14 @@ struct TileArgs {
     FieldPtrs F;
     GridGeom G;
     StaggeredCoefs C;
+    MediaPtrs MD;     // heterogeneous mode (HET kernels, fp32): per-cell media, see hetero.cuh
+    HeteroCoefs HC;
     int t0, t1;
     int xchunk;
 };
 
 // stress pass: T[t1] = T[t0] + windows of U,V,W[t0]
-template <int SO, typename T, int ARITH>
+template <int SO, typename T, int ARITH, bool HET = false>
 __global__ void __launch_bounds__(TileCfg<SO / 2, T>::THREADS)
 stress_tiled(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
              const __grid_constant__ CUtensorMap tmW, const TileArgs A)
@@ -101,6 +104,13 @@ stress_tiled(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CU
     T told[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) told[k] = T0[k][(long long)xa * sx];
+    // heterogeneous mode: lambda, mu, mu12, mu23, mu13 of the own cell, loaded one plane ahead like T[t0]
+    const int MID[5] = {OPESCI_MEDIA_LAMBDA, OPESCI_MEDIA_MU, OPESCI_MEDIA_MU12, OPESCI_MEDIA_MU23, OPESCI_MEDIA_MU13};
+    float mnext[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (HET) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) mnext[k] = A.MD.m[MID[k]][col + (long long)xa * sx];
+    }
     const int ctr = (ty + M) * VZ + tz + M;   // own element inside a tile
     for (int x = xa, it = 0; x < xb; ++x, ++it) {
         const int slot = it % NB;
@@ -119,6 +129,13 @@ stress_tiled(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CU
 #pragma unroll
             for (int k = 0; k < 6; ++k) told[k] = T0[k][px + sx];
         }
+        float med[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) med[k] = mnext[k];
+        if (HET && x + 1 < xb) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) mnext[k] = A.MD.m[MID[k]][col + px + sx];
+        }
         mbar_wait(&bars[0 * NB + slot], par);
         mbar_wait(&bars[1 * NB + slot], par);
         mbar_wait(&bars[2 * NB + slot], par);
@@ -136,7 +153,52 @@ stress_tiled(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CU
             vzf[j] = sv[j - M + 1];
         }
         T out[6];
-        if (ARITH == OPESCI_ARITH_REFERENCE) {
+        if constexpr (HET) {
+            // per-cell media: every term is (literal*G)*media in reference arithmetic, factored in fast arithmetic
+            const float lam = med[0], mu = med[1];
+            if (ARITH == OPESCI_ARITH_REFERENCE) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    float acc = tcur[a];
+                    bool first = false;
+                    if (a == 0) window_ref_arr_h<M, false, 2>(acc, first, uw, A.HC.c[0], A.HC.c2[0], lam, mu);
+                    else window_ref_arr_h<M, false, 1>(acc, first, uw, A.HC.c[0], A.HC.c2[0], lam, mu);
+                    if (a == 1) window_ref_arr_h<M, false, 2>(acc, first, vy, A.HC.c[1], A.HC.c2[1], lam, mu);
+                    else window_ref_arr_h<M, false, 1>(acc, first, vy, A.HC.c[1], A.HC.c2[1], lam, mu);
+                    if (a == 2) window_ref_arr_h<M, false, 2>(acc, first, wzb, A.HC.c[2], A.HC.c2[2], lam, mu);
+                    else window_ref_arr_h<M, false, 1>(acc, first, wzb, A.HC.c[2], A.HC.c2[2], lam, mu);
+                    out[a] = acc;
+                }
+                {
+                    float acc = tcur[3]; bool first = false;   // Txy (mu12)
+                    window_ref_arr_h<M, true, 1>(acc, first, uy, A.HC.c[1], A.HC.c2[1], med[2], 0.f);
+                    window_ref_arr_h<M, true, 1>(acc, first, vw, A.HC.c[0], A.HC.c2[0], med[2], 0.f);
+                    out[3] = acc;
+                }
+                {
+                    float acc = tcur[4]; bool first = false;   // Tyz (mu23)
+                    window_ref_arr_h<M, true, 1>(acc, first, vzf, A.HC.c[2], A.HC.c2[2], med[3], 0.f);
+                    window_ref_arr_h<M, true, 1>(acc, first, wy, A.HC.c[1], A.HC.c2[1], med[3], 0.f);
+                    out[4] = acc;
+                }
+                {
+                    float acc = tcur[5]; bool first = false;   // Txz (mu13)
+                    window_ref_arr_h<M, true, 1>(acc, first, uzf, A.HC.c[2], A.HC.c2[2], med[4], 0.f);
+                    window_ref_arr_h<M, true, 1>(acc, first, ww, A.HC.c[0], A.HC.c2[0], med[4], 0.f);
+                    out[5] = acc;
+                }
+            } else {
+                const T du = window_fast_arr<M, T, false>(uw, A.HC.c[0]), dv = window_fast_arr<M, T, false>(vy, A.HC.c[1]),
+                        dw = window_fast_arr<M, T, false>(wzb, A.HC.c[2]);
+                const T tr = lam * (du + dv + dw), mu2 = 2.0f * mu;
+                out[0] = tcur[0] + (tr + mu2 * du);
+                out[1] = tcur[1] + (tr + mu2 * dv);
+                out[2] = tcur[2] + (tr + mu2 * dw);
+                out[3] = tcur[3] + med[2] * (window_fast_arr<M, T, true>(uy, A.HC.c[1]) + window_fast_arr<M, T, true>(vw, A.HC.c[0]));
+                out[4] = tcur[4] + med[3] * (window_fast_arr<M, T, true>(vzf, A.HC.c[2]) + window_fast_arr<M, T, true>(wy, A.HC.c[1]));
+                out[5] = tcur[5] + med[4] * (window_fast_arr<M, T, true>(uzf, A.HC.c[2]) + window_fast_arr<M, T, true>(ww, A.HC.c[0]));
+            }
+        } else if (ARITH == OPESCI_ARITH_REFERENCE) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 T acc = tcur[a];
@@ -189,7 +251,7 @@ stress_tiled(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CU
 }
 
 // velocity pass: V[t1] = windows of T[t1] + V[t0].  Tiles: Txy, Tyy, Tyz, Txz, Tzz; x-windows: Txx, Txy, Txz.
-template <int SO, typename T, int ARITH>
+template <int SO, typename T, int ARITH, bool HET = false>
 __global__ void __launch_bounds__(TileCfg<SO / 2, T>::THREADS)
 velocity_tiled(const __grid_constant__ CUtensorMap tmXY, const __grid_constant__ CUtensorMap tmYY,
                const __grid_constant__ CUtensorMap tmYZ, const __grid_constant__ CUtensorMap tmXZ,
@@ -242,6 +304,11 @@ velocity_tiled(const __grid_constant__ CUtensorMap tmXY, const __grid_constant__
     T snext[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) snext[k] = ((const T *)A.F.f[F_U + k])[l0 + (long long)xa * sx];
+    float bnext[3] = {0.f, 0.f, 0.f};   // heterogeneous mode: beta1, beta2, beta3 of the own cell, one plane ahead
+    if (HET) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bnext[k] = A.MD.m[OPESCI_MEDIA_BETA1 + k][col + (long long)xa * sx];
+    }
     const int ctr = (ty + M) * VZ + tz + M;
     for (int x = xa, it = 0; x < xb; ++x, ++it) {
         const int slot = it % NB;
@@ -260,6 +327,13 @@ velocity_tiled(const __grid_constant__ CUtensorMap tmXY, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < 3; ++k) snext[k] = ((const T *)A.F.f[F_U + k])[l0 + px + sx];
         }
+        float bet[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bet[k] = bnext[k];
+        if (HET && x + 1 < xb) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) bnext[k] = A.MD.m[OPESCI_MEDIA_BETA1 + k][col + px + sx];
+        }
 #pragma unroll
         for (int f = 0; f < 5; ++f) mbar_wait(&bars[f * NB + slot], par);
         const T *sxy = ring + (size_t)(0 * NB + slot) * TE + ctr, *syy = ring + (size_t)(1 * NB + slot) * TE + ctr;
@@ -276,7 +350,32 @@ velocity_tiled(const __grid_constant__ CUtensorMap tmXY, const __grid_constant__
             zz_z[j] = szz[j - M + 1];          // Tzz forward in z (W)
         }
         T out[3];
-        if (ARITH == OPESCI_ARITH_REFERENCE) {
+        if constexpr (HET) {
+            if (ARITH == OPESCI_ARITH_REFERENCE) {
+                float acc = 0; bool first = true;
+                window_ref_arr_h<M, true, 1>(acc, first, xx, A.HC.c[0], A.HC.c2[0], bet[0], 0.f);
+                window_ref_arr_h<M, false, 1>(acc, first, xy_y, A.HC.c[1], A.HC.c2[1], bet[0], 0.f);
+                window_ref_arr_h<M, false, 1>(acc, first, xz_z, A.HC.c[2], A.HC.c2[2], bet[0], 0.f);
+                out[0] = __fadd_rn(acc, self[0]);
+                acc = 0; first = true;
+                window_ref_arr_h<M, false, 1>(acc, first, xy, A.HC.c[0], A.HC.c2[0], bet[1], 0.f);
+                window_ref_arr_h<M, true, 1>(acc, first, yy_y, A.HC.c[1], A.HC.c2[1], bet[1], 0.f);
+                window_ref_arr_h<M, false, 1>(acc, first, yz_z, A.HC.c[2], A.HC.c2[2], bet[1], 0.f);
+                out[1] = __fadd_rn(acc, self[1]);
+                acc = 0; first = true;
+                window_ref_arr_h<M, false, 1>(acc, first, xz, A.HC.c[0], A.HC.c2[0], bet[2], 0.f);
+                window_ref_arr_h<M, false, 1>(acc, first, yz_y, A.HC.c[1], A.HC.c2[1], bet[2], 0.f);
+                window_ref_arr_h<M, true, 1>(acc, first, zz_z, A.HC.c[2], A.HC.c2[2], bet[2], 0.f);
+                out[2] = __fadd_rn(acc, self[2]);
+            } else {
+                out[0] = self[0] + bet[0] * (window_fast_arr<M, T, true>(xx, A.HC.c[0]) + window_fast_arr<M, T, false>(xy_y, A.HC.c[1]) +
+                                             window_fast_arr<M, T, false>(xz_z, A.HC.c[2]));
+                out[1] = self[1] + bet[1] * (window_fast_arr<M, T, false>(xy, A.HC.c[0]) + window_fast_arr<M, T, true>(yy_y, A.HC.c[1]) +
+                                             window_fast_arr<M, T, false>(yz_z, A.HC.c[2]));
+                out[2] = self[2] + bet[2] * (window_fast_arr<M, T, false>(xz, A.HC.c[0]) + window_fast_arr<M, T, false>(yz_y, A.HC.c[1]) +
+                                             window_fast_arr<M, T, true>(zz_z, A.HC.c[2]));
+            }
+        } else if (ARITH == OPESCI_ARITH_REFERENCE) {
             T acc = 0; bool first = true;
             window_ref_arr<M, T, true>(acc, first, xx, A.C.v[0][0]);
             window_ref_arr<M, T, false>(acc, first, xy_y, A.C.v[0][1]);
