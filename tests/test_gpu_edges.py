@@ -1,0 +1,65 @@
+"""GPU: edge cases of the hot path, CUDA (reference arithmetic, through the C ABI) against the oracle bit for bit.
+
+The reference has no unit tests; these cover what its loops do at the corners of their domain:
+zero and one time step (time-level parity `ti = ntsteps % 2`), grids barely larger than the stencil, sizes that are
+not multiples of any tile, every kernel family (fused so<=4, TMA-tiled so>=6 / fp64, regular acoustic incl. the
+marching kernel), and heterogeneous media on ragged sizes."""
+import numpy as np
+import pytest
+
+from common import bits, fields_of, make_grid
+from opesci_fd_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # kind, so, grid_size, steps, double
+    ("eigenwave3d", 4, [30, 28, 34], 0, False),      # no step at all: init + initial BC pass only
+    ("eigenwave3d", 4, [30, 28, 34], 1, False),      # one step: results live on level 1
+    ("eigenwave3d", 4, [1, 1, 1], 3, False),         # smallest legal grid (dim = 6): 2 interior points per axis
+    ("eigenwave3d", 2, [2, 1, 3], 4, False),
+    ("eigenwave3d", 12, [3, 2, 1], 3, False),        # dim 16 x 15 x 14 with m = 6
+    ("eigenwave3d", 2, [61, 45, 67], 6, False),      # so=2 through the fused kernel, ragged sizes
+    ("eigenwave3d", 4, [129, 17, 63], 5, False),     # long in x, thin in y
+    ("eigenwave3d", 4, [17, 131, 12], 5, False),     # z shorter than one tile
+    ("eigenwave3d", 6, [37, 41, 43], 5, False),      # tiled kernels, odd m
+    ("eigenwave3d", 10, [40, 33, 70], 4, True),      # tiled kernels, fp64, odd m
+    ("eigenwave3d", 12, [45, 38, 36], 4, True),
+    ("eigenwave3d", 4, [50, 44, 48], 7, True),       # so=4 fp64: tiled, Levander
+    ("simplewave3d", 2, [33, 29, 31], 9, False),
+    ("simplewave3d", 12, [40, 37, 35], 8, True),
+    ("simplewave3d", 8, [2, 2, 2], 5, False),
+    ("eigenwave3d_read", 4, [35, 67, 29], 9, False),  # heterogeneous, fused
+    ("eigenwave3d_read", 2, [31, 30, 40], 6, False),
+    ("eigenwave3d_read", 6, [33, 36, 34], 5, False),  # heterogeneous, tiled, Robertsson
+    ("eigenwave3d_read", 4, [2, 3, 1], 3, False),     # heterogeneous on a minimal grid
+]
+
+
+@pytest.mark.parametrize("kind,so,size,steps,double", CASES)
+def test_cuda_equals_oracle_on_edge_cases(kind, so, size, steps, double, cuda_lib, oracle_lib):
+    cfg = dict(kind=kind, so=so, grid_size=size, dt=0.0015, steps=steps, double=double,
+               domain=[1.0, 0.9, 1.2], rho=1.1, vp=1.9, vs=1.0, seed=3)
+    a, b = make_grid(cfg, flags=abi.ARITH_REFERENCE | abi.HOST_MIRROR_FULL), make_grid(cfg)
+    a.run(library=cuda_lib)
+    b.run(library=oracle_lib)
+    fa, fb = fields_of(a), fields_of(b)
+    assert fa.shape == fb.shape
+    assert not np.isnan(fb).any()
+    assert int((bits(fa) != bits(fb)).sum()) == 0
+    np.testing.assert_allclose(a.convergence_f64(), b.convergence_f64(), rtol=1e-12, atol=0)
+    a.free()
+    b.free()
+
+
+def test_fast_arithmetic_on_device_pointers(cuda_lib):
+    """HOST_MIRROR_NONE: grid->field[] are device pointers; opesci_convergence reduces on the device and equals the
+    host-mirror run of the same model."""
+    cfg = dict(kind="eigenwave3d", so=4, grid_size=[48, 40, 52], dt=0.002, steps=10, double=False, domain=[1.0, 1.0, 1.0])
+    a = make_grid(cfg, flags=abi.ARITH_FAST | abi.HOST_MIRROR_NONE)
+    b = make_grid(cfg, flags=abi.ARITH_FAST | abi.HOST_MIRROR_FULL)
+    a.run(library=cuda_lib)
+    b.run(library=cuda_lib)
+    assert a.convergence_f64() == b.convergence_f64()
+    a.free()
+    b.free()
