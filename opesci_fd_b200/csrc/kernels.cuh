@@ -272,11 +272,18 @@ acoustic_march(FieldPtrs F, GridGeom G, AcousticCoefs C, int tprev, int tr, int 
     float4 win[2 * M + 1];   // planes x-M .. x+M of the own column
 #pragma unroll
     for (int j = 0; j < 2 * M; ++j) win[j + 1] = *reinterpret_cast<const float4 *>(r1 + (long long)(xa - M + j) * sx);
+    // software pipeline: the two compulsory loads of plane x+1 are issued before the arithmetic of plane x
+    float4 nwin = *reinterpret_cast<const float4 *>(r1 + (long long)(xa + M) * sx);
+    float4 nprev = *reinterpret_cast<const float4 *>(r0 + (long long)xa * sx);
     for (int x = xa; x < xb; ++x) {
 #pragma unroll
         for (int j = 0; j < 2 * M; ++j) win[j] = win[j + 1];
-        win[2 * M] = *reinterpret_cast<const float4 *>(r1 + (long long)(x + M) * sx);
-        const float4 prev = *reinterpret_cast<const float4 *>(r0 + (long long)x * sx);
+        win[2 * M] = nwin;
+        const float4 prev = nprev;
+        if (x + 1 < xb) {
+            nwin = *reinterpret_cast<const float4 *>(r1 + (long long)(x + 1 + M) * sx);
+            nprev = *reinterpret_cast<const float4 *>(r0 + (long long)(x + 1) * sx);
+        }
         float4 yn[2 * M];    // rows y+1..y+M, then y-1..y-M of the centre plane
 #pragma unroll
         for (int o = 1; o <= M; ++o) {

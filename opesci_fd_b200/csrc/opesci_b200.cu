@@ -499,7 +499,7 @@ struct Stepper {
                     const Model &Md = R.M;
                     const int nx = Md.G.dim[0] - 2 * Md.m, ny = Md.G.dim[1] - 2 * Md.m;
                     const int nbz = (int)((Md.G.s[1] / 4 + 31) / 32), nby = (ny + 7) / 8;
-                    int nchunks = (4 * 148 + nbz * nby - 1) / (nbz * nby);   // >= 4 blocks per SM in flight
+                    int nchunks = (8 * 148 + nbz * nby - 1) / (nbz * nby);   // >= 8 blocks per SM in flight
                     if (nchunks < 1) nchunks = 1;
                     if (nchunks > nx / (4 * Md.m) && nx / (4 * Md.m) >= 1) nchunks = nx / (4 * Md.m);
                     const int xchunk = (nx + nchunks - 1) / nchunks;
