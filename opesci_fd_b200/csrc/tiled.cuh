@@ -30,6 +30,16 @@ template <int M, typename T> struct TileCfg {
     static constexpr int NB = 3;                                // ring depth (planes)
     static constexpr int TILE = ((VZ * VY * (int)sizeof(T) + 127) / 128) * 128;   // bytes, 128-B aligned for TMA
     static constexpr int THREADS = TY * TZ;
+#ifndef OPESCI_TILED_MINB_F64
+#define OPESCI_TILED_MINB_F64 2
+#endif
+#ifndef OPESCI_TILED_MINB_F32
+#define OPESCI_TILED_MINB_F32 1
+#endif
+    // resident CTAs per SM the register allocation must leave room for: the fp64 kernels otherwise take
+    // 160+ registers (every window array live at once) and run with a single 8-warp CTA per SM
+    // (so=8 fp64 768^3: 15.7 -> 19.8 Gpts/s; at m >= 5 the 128-register cap spills and loses)
+    static constexpr int MINB = (sizeof(T) == 8 && M <= 4) ? OPESCI_TILED_MINB_F64 : OPESCI_TILED_MINB_F32;
     static constexpr int smem(int nfields) { return nfields * NB * TILE + nfields * NB * 8 + 128; }
 };
 
@@ -45,7 +55,7 @@ struct TileArgs {
 
 // stress pass: T[t1] = T[t0] + windows of U,V,W[t0]
 template <int SO, typename T, int ARITH, bool HET = false>
-__global__ void __launch_bounds__(TileCfg<SO / 2, T>::THREADS)
+__global__ void __launch_bounds__(TileCfg<SO / 2, T>::THREADS, TileCfg<SO / 2, T>::MINB)
 stress_tiled(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
              const __grid_constant__ CUtensorMap tmW, const TileArgs A)
 {
@@ -252,7 +262,7 @@ stress_tiled(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CU
 
 // velocity pass: V[t1] = windows of T[t1] + V[t0].  Tiles: Txy, Tyy, Tyz, Txz, Tzz; x-windows: Txx, Txy, Txz.
 template <int SO, typename T, int ARITH, bool HET = false>
-__global__ void __launch_bounds__(TileCfg<SO / 2, T>::THREADS)
+__global__ void __launch_bounds__(TileCfg<SO / 2, T>::THREADS, TileCfg<SO / 2, T>::MINB)
 velocity_tiled(const __grid_constant__ CUtensorMap tmXY, const __grid_constant__ CUtensorMap tmYY,
                const __grid_constant__ CUtensorMap tmYZ, const __grid_constant__ CUtensorMap tmXZ,
                const __grid_constant__ CUtensorMap tmZZ, const TileArgs A)
