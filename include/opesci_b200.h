@@ -190,6 +190,22 @@ typedef struct OpesciB200Params {
                                       * as `*lambda*mu/D` terms */
     float h_vn[3][2];                /* velocity normal ghost, [axis g]: P_g and 2 P_g */
 
+    /* ---- point source + receivers.  Not part of the generated code: the semantics are those of
+     * the reference's hand-written propagator (tests/src/test_ref_iso_elastic.cpp:227-290).  At the end of time step
+     * ti (after the velocity ghost loops):
+     *   1. receiver r samples U, V, W and (Txx+Tyy+Tzz)/3 of the new time level at its grid cell
+     *      -> receiver_out[((ti*4 + c)*n_receivers) + r], c = 0..3, real_t;
+     *   2. if ti < src_nt: Txx, Tyy, Tzz[new level][source cell] -= src_x|y|z[ti]/3   (explosive source).
+     * Cells are array indices (x,y,z) including the ghost margin m: round(coordinate/dx_d) + m.  Staggered elastic
+     * model only.  With slabs every rank handles the cells on planes it owns; other receivers read 0. */
+    int32_t n_receivers;
+    int32_t src_nt;                   /* 0: no source */
+    int32_t source_cell[3];
+    int32_t reserved2_;
+    const int32_t *receiver_cells;    /* HOST [n_receivers][3] */
+    const float *src_x, *src_y, *src_z;   /* HOST [src_nt] each */
+    void *receiver_out;               /* HOST [ntsteps][4][n_receivers] real_t, filled by opesci_execute */
+
     OpesciFieldSpec fields[OPESCI_MAX_FIELDS];
 } OpesciB200Params;
 

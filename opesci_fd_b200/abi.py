@@ -89,6 +89,10 @@ class OpesciB200Params(Structure):
         ("h_lev_own", ((c_float * 2) * 3) * 3),
         ("h_lev_oth", ((c_float * 2) * 3) * 3),
         ("h_vn", (c_float * 2) * 3),
+        ("n_receivers", c_int32), ("src_nt", c_int32), ("source_cell", c_int32 * 3), ("reserved2_", c_int32),
+        ("receiver_cells", POINTER(c_int32)),
+        ("src_x", POINTER(c_float)), ("src_y", POINTER(c_float)), ("src_z", POINTER(c_float)),
+        ("receiver_out", c_void_p),
         ("fields", OpesciFieldSpec * OPESCI_MAX_FIELDS),
     ]
 

@@ -475,6 +475,47 @@ face_batch(const __grid_constant__ FieldPtrs F, const __grid_constant__ GridGeom
     }
 }
 
+// ------------------------------------------------------------------ point source + receivers
+// Semantics of the reference's hand-written propagator (tests/src/test_ref_iso_elastic.cpp:227-290), run at the end of
+// a time step: receivers sample U, V, W and the mean normal stress of the new level; then the explosive source is
+// subtracted from the normal stresses.  `*step` counts the time steps on the device, so both kernels replay from a
+// CUDA graph.  Offsets < 0 mark cells this rank does not own.
+template <typename T>
+__global__ void sample_receivers(FieldPtrs F, long long level_off, const long long *__restrict__ cell, int n, T *__restrict__ out,
+                                 const int *__restrict__ step)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int ti = *step;
+    const long long c = cell[r];
+    T v[4] = {0, 0, 0, 0};
+    if (c >= 0) {
+        const long long q = level_off + c;
+        v[0] = ((const T *)F.f[F_U])[q];
+        v[1] = ((const T *)F.f[F_V])[q];
+        v[2] = ((const T *)F.f[F_W])[q];
+        const T s = add_rn<T>(add_rn<T>(((const T *)F.f[F_TXX])[q], ((const T *)F.f[F_TYY])[q]), ((const T *)F.f[F_TZZ])[q]);
+        v[3] = s / (T)3;   // IEEE division (no fast-math)
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[((size_t)ti * 4 + k) * n + r] = v[k];
+}
+
+template <typename T>
+__global__ void inject_source(FieldPtrs F, long long level_off, long long cell, const float *__restrict__ sx, const float *__restrict__ sy,
+                              const float *__restrict__ sz, int src_nt, int *__restrict__ step)
+{
+    const int ti = *step;
+    if (ti < src_nt && cell >= 0) {
+        const long long q = level_off + cell;
+        T *txx = (T *)F.f[F_TXX], *tyy = (T *)F.f[F_TYY], *tzz = (T *)F.f[F_TZZ];
+        txx[q] = add_rn<T>(txx[q], -(T)__fdiv_rn(sx[ti], 3.0f));
+        tyy[q] = add_rn<T>(tyy[q], -(T)__fdiv_rn(sy[ti], 3.0f));
+        tzz[q] = add_rn<T>(tzz[q], -(T)__fdiv_rn(sz[ti], 3.0f));
+    }
+    *step = ti + 1;
+}
+
 // ------------------------------------------------------------------ analytic programs
 struct DevProgram {
     int n_instr, n_tables;

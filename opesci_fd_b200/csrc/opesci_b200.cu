@@ -123,6 +123,13 @@ struct Run {
     void *dev[OPESCI_MAX_FIELDS] = {};
     void *host[OPESCI_MAX_FIELDS] = {};
     float *media[OPESCI_MEDIA_COUNT] = {};   // heterogeneous mode: derived media arrays (one level each)
+    // point source + receivers
+    bool hooks = false;
+    long long *d_recv_cell = nullptr;   // [n_receivers] element offsets inside one level, -1 = not owned
+    void *d_recv_out = nullptr;         // [ntsteps][4][n_receivers] real_t
+    float *d_src = nullptr;             // [3][src_nt]
+    int *d_step = nullptr;              // time-step counter on the device
+    long long src_cell = -1;
     bool host_pinned = false;
     double *d_tables = nullptr;
     DevProgram *d_prog = nullptr;   // [nfields][2]
@@ -748,6 +755,20 @@ struct Stepper {
         }
     }
 
+    // receivers, then the source, at the end of a step (kernels.cuh); the device keeps the step count
+    template <typename T> void point_hooks(int t1)
+    {
+        if (!R.hooks) return;
+        const OpesciB200Params &p = R.M.p;
+        const long long lvl = (long long)t1 * R.M.G.level;
+        if (p.n_receivers > 0) {
+            sample_receivers<T><<<(p.n_receivers + 127) / 128, 128, 0, st>>>(ptrs(), lvl, R.d_recv_cell, p.n_receivers, (T *)R.d_recv_out, R.d_step);
+            check();
+        }
+        inject_source<T><<<1, 1, 0, st>>>(ptrs(), lvl, R.src_cell, R.d_src, R.d_src + p.src_nt, R.d_src + 2 * (size_t)p.src_nt, p.src_nt, R.d_step);
+        check();
+    }
+
     template <int SO, typename T, int ARITH> void staggered_step(int ti)
     {
         const int t0 = ti % 2, t1 = (t0 + 1) % 2;   // opesci/regulargrid.py:408-433
@@ -762,6 +783,7 @@ struct Stepper {
             velocity<SO, T, ARITH>(t0, t1);
             velocity_bc<T>(t1);
         }
+        point_hooks<T>(t1);
     }
     template <int SO, typename T, int ARITH> void acoustic_step(int ti)
     {
@@ -995,6 +1017,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
             X.template stress_bc<T>(t0, t1, false);
             X.template velocity_shell<SO, T, ARITH>(t0, t1);
             X.template velocity_bc<T>(t1);
+            X.template point_hooks<T>(t1);
         };
         auto step = [&](int ti, bool has_prev) -> int {
             const int t0 = ti % 2, t1 = (t0 + 1) % 2;
@@ -1065,6 +1088,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
             S.template stress_bc<T>(t0, t1, false);
             S.template velocity_shell<SO, T, ARITH>(t0, t1);
             S.template velocity_bc<T>(t1);
+            S.template point_hooks<T>(t1);
             CUDA_OK(cudaEventRecord(ev_fork, st));
             CUDA_OK(cudaStreamWaitEvent(st2, ev_fork, 0));
             if (exchange(t1, st2)) return 1;
@@ -1225,6 +1249,10 @@ void release(Run *R)
         if (R->media[k]) cudaFree(R->media[k]);
     if (R->d_tables) cudaFree(R->d_tables);
     if (R->d_prog) cudaFree(R->d_prog);
+    if (R->d_recv_cell) cudaFree(R->d_recv_cell);
+    if (R->d_recv_out) cudaFree(R->d_recv_out);
+    if (R->d_src) cudaFree(R->d_src);
+    if (R->d_step) cudaFree(R->d_step);
     delete R;
 }
 
@@ -1299,6 +1327,40 @@ int setup_media(Run &R, cudaStream_t st)
     cudaError_t e = cudaStreamSynchronize(st);
     cleanup();
     if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return fail("heterogeneous media: kernels failed (%s)", cudaGetErrorString(e));
+    return 0;
+}
+
+// point source + receivers: device copies of the cell offsets and the source time series
+int setup_hooks(Run &R)
+{
+    const Model &M = R.M;
+    const OpesciB200Params &p = M.p;
+    R.hooks = p.n_receivers > 0 || p.src_nt > 0;
+    if (!R.hooks) return 0;
+    const size_t esz = p.is_double ? 8 : 4;
+    auto offset = [&](const int32_t *c) -> long long {
+        if (c[0] < M.slab.own_lo || c[0] >= M.slab.own_hi) return -1;   // another rank's plane
+        return (long long)(c[0] - M.slab.L0) * M.G.s[0] + (long long)c[1] * M.G.s[1] + c[2];
+    };
+    CUDA_OK(cudaMalloc(&R.d_step, sizeof(int)));
+    CUDA_OK(cudaMemset(R.d_step, 0, sizeof(int)));
+    if (p.n_receivers > 0) {
+        std::vector<long long> cells(p.n_receivers);
+        for (int r = 0; r < p.n_receivers; ++r) cells[r] = offset(p.receiver_cells + 3 * r);
+        CUDA_OK(cudaMalloc(&R.d_recv_cell, cells.size() * sizeof(long long)));
+        CUDA_OK(cudaMemcpy(R.d_recv_cell, cells.data(), cells.size() * sizeof(long long), cudaMemcpyHostToDevice));
+        const size_t bytes = (size_t)(p.ntsteps > 0 ? p.ntsteps : 1) * 4 * p.n_receivers * esz;
+        CUDA_OK(cudaMalloc(&R.d_recv_out, bytes));
+        CUDA_OK(cudaMemset(R.d_recv_out, 0, bytes));
+    }
+    R.src_cell = p.src_nt > 0 ? offset(p.source_cell) : -1;
+    const size_t nsrc = p.src_nt > 0 ? p.src_nt : 1;
+    CUDA_OK(cudaMalloc(&R.d_src, 3 * nsrc * sizeof(float)));
+    if (p.src_nt > 0) {
+        CUDA_OK(cudaMemcpy(R.d_src, p.src_x, p.src_nt * sizeof(float), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(R.d_src + p.src_nt, p.src_y, p.src_nt * sizeof(float), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(R.d_src + 2 * (size_t)p.src_nt, p.src_z, p.src_nt * sizeof(float), cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -1463,6 +1525,17 @@ int opesci_b200_configure(const OpesciB200Params *params)
             OpesciSolProgram &pr = w ? M.p.fields[f].final_ : M.p.fields[f].init;
             for (int t = 0; t < OPESCI_MAX_TABLES; ++t) pr.table[t] = nullptr;   // host pointers are not kept
         }
+    if ((params->n_receivers > 0 || params->src_nt > 0) && params->kind != OPESCI_KIND_STAGGERED_ELASTIC)
+        return fail("point source / receivers: staggered elastic model only");
+    if ((params->n_receivers > 0 && (!params->receiver_cells || !params->receiver_out)) ||
+        (params->src_nt > 0 && (!params->src_x || !params->src_y || !params->src_z)))
+        return fail("point source / receivers: null array");
+    for (int r = 0; r < params->n_receivers; ++r)
+        for (int d = 0; d < 3; ++d)
+            if (params->receiver_cells[3 * r + d] < 0 || params->receiver_cells[3 * r + d] >= params->dim[d]) return fail("receiver cell outside the grid");
+    if (params->src_nt > 0)
+        for (int d = 0; d < 3; ++d)
+            if (params->source_cell[d] < 0 || params->source_cell[d] >= params->dim[d]) return fail("source cell outside the grid");
     if (params->kind == OPESCI_KIND_STAGGERED_ELASTIC) {
         if (params->nfields != 9 || params->nlevels != 2) return fail("staggered: need 9 fields, 2 levels");
         if (params->hetero) {
@@ -1510,9 +1583,13 @@ int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
     if (upload_programs(*R)) return bail(1);
     if (setup_fused(*R)) return bail(1);
     if (setup_tiled(*R)) return bail(1);
+    if (setup_hooks(*R)) return bail(1);
     double secs = 0.0;
     if (dispatch(*R, st, &secs)) return bail(1);
     g_loop_seconds = secs;
+    if (p.n_receivers > 0 && p.receiver_out && p.ntsteps > 0 &&
+        cudaMemcpy(p.receiver_out, R->d_recv_out, (size_t)p.ntsteps * 4 * p.n_receivers * esz, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return bail(fail("opesci_execute: copying the receiver data back failed"));
     const int mirror = p.flags & OPESCI_HOST_MIRROR_MASK;
     if (mirror == OPESCI_HOST_MIRROR_FULL) {
         for (int f = 0; f < p.nfields; ++f) {

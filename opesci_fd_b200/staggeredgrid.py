@@ -198,6 +198,53 @@ class StaggeredGrid(RegularGrid):
                 raise ValueError("media arrays must be [nplanes][dim2][dim3] = [*][%d][%d]" % (dims[1], dims[2]))
         return self.media_arrays
 
+    # ------------------------------------------------------------------ point source + receivers
+    def _cell_of(self, coord):
+        """grid node nearest to a coordinate, as an array index: round(coordinate/dx_d) + m
+        (the reference's hand-written propagator uses round(coord/h), tests/src/test_ref_iso_elastic.cpp:229-231)"""
+        m = self.margin.value
+        return [int(round(float(c) / float(sp.value))) + m for c, sp in zip(coord, self.spacing)]
+
+    def set_receivers(self, coordinates):
+        """B200 addition: every receiver records U, V, W and (Txx+Tyy+Tzz)/3 at its nearest
+        grid node at the end of every time step; read them with `receiver_data()` after `execute`/`run`."""
+        self._receivers = [self._cell_of(c) for c in coordinates]
+
+    def set_source(self, coordinate, xsrc, ysrc=None, zsrc=None):
+        """Explosive point source: Txx, Tyy, Tzz[node] -= x|y|zsrc[ti]/3 at the end of step ti
+        (tests/src/test_ref_iso_elastic.cpp:276-290)."""
+        xs = np.ascontiguousarray(xsrc, dtype=np.float32)
+        ys = xs if ysrc is None else np.ascontiguousarray(ysrc, dtype=np.float32)
+        zs = xs if zsrc is None else np.ascontiguousarray(zsrc, dtype=np.float32)
+        if not (xs.shape == ys.shape == zs.shape) or xs.ndim != 1:
+            raise ValueError("source time series must be 1-D and of equal length")
+        self._source = (self._cell_of(coordinate), xs, ys, zs)
+
+    def receiver_data(self):
+        """[ntsteps][4][n_receivers] array (U, V, W, mean normal stress) recorded by the last run."""
+        return getattr(self, '_receiver_out', None)
+
+    def _lower_hooks(self, p, keep):
+        rec = getattr(self, '_receivers', None)
+        src = getattr(self, '_source', None)
+        self._receiver_out = None
+        if rec:
+            cells = np.ascontiguousarray(np.array(rec, dtype=np.int32).reshape(-1, 3))
+            out = np.zeros((max(self.ntsteps.value, 1), 4, len(rec)), dtype=np.float64 if self.double else np.float32)
+            p.n_receivers = len(rec)
+            p.receiver_cells = cells.ctypes.data_as(abi.POINTER(abi.c_int32))
+            p.receiver_out = out.ctypes.data_as(abi.c_void_p)
+            self._receiver_out = out
+            keep += [cells, out]
+        if src:
+            cell, xs, ys, zs = src
+            p.src_nt = int(xs.shape[0])
+            for d in range(3):
+                p.source_cell[d] = cell[d]
+            fptr = abi.POINTER(abi.c_float)
+            p.src_x, p.src_y, p.src_z = xs.ctypes.data_as(fptr), ys.ctypes.data_as(fptr), zs.ctypes.data_as(fptr)
+            keep += [xs, ys, zs]
+
     def set_free_surface_boundary(self, dimension, side):
         """reference: staggeredgrid.py:214-232.  Levander for so == 4, Robertsson otherwise."""
         self._free_surface.add((dimension, side))
@@ -256,6 +303,7 @@ class StaggeredGrid(RegularGrid):
             for k in range(m):
                 dst[k] = literal(float(ck[k] * dt / dx[d] * coef))
 
+        self._lower_hooks(p, keep)
         if self.read:
             self._lower_hetero(p, keep, vel, normal, shear, ck, dt, dx, m, so, pde)
         # interior updates

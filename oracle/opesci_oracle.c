@@ -548,6 +548,14 @@ int opesci_b200_configure(const OpesciB200Params *params)
         fs->l2_lo[0] = (fs->l2_lo[0] > sl->own_lo ? fs->l2_lo[0] : sl->own_lo) - sl->L0;
         fs->l2_hi[0] = (fs->l2_hi[0] < sl->own_hi ? fs->l2_hi[0] : sl->own_hi) - sl->L0;
     }
+    if ((params->n_receivers > 0 || params->src_nt > 0) && params->kind != OPESCI_KIND_STAGGERED_ELASTIC)
+        return fail("point source / receivers: staggered elastic model only");
+    for (int r = 0; r < params->n_receivers; ++r)
+        for (int d = 0; d < 3; ++d)
+            if (params->receiver_cells[3 * r + d] < 0 || params->receiver_cells[3 * r + d] >= params->dim[d]) return fail("receiver cell outside the grid");
+    if (params->src_nt > 0)
+        for (int d = 0; d < 3; ++d)
+            if (params->source_cell[d] < 0 || params->source_cell[d] >= params->dim[d]) return fail("source cell outside the grid");
     if (params->kind == OPESCI_KIND_STAGGERED_ELASTIC) {
         if (params->nfields != 9 || params->nlevels != 2) return fail("staggered: need 9 fields, 2 levels");
         if (params->hetero && params->is_double) return fail("heterogeneous media: fp32 only (the reader is float*)");

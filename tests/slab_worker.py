@@ -69,6 +69,9 @@ def main():
         assert lib.opesci_b200_slab_range(rank, world, grid.dim[0].value, cfg["so"], ctypes.byref(l0), ctypes.byref(l1)) == 0
         rho, vp, vs = grid.media_arrays
         grid.set_media_arrays(rho[l0.value:l1.value], vp[l0.value:l1.value], vs[l0.value:l1.value], plane0=l0.value)
+    if cfg.get("hooks"):
+        grid.set_receivers(cfg["hooks"]["receivers"])
+        grid.set_source(cfg["hooks"]["source"], np.array(cfg["hooks"]["wavelet"], dtype=np.float32))
     orig = grid.build_params
 
     def with_slab():
@@ -96,7 +99,9 @@ def main():
         fields.append(np.frombuffer(buf, dtype=np.float64 if p.is_double else np.float32).reshape(
             p.nlevels, L1 - L0, p.dim[1], p.dim[2]).copy())
     l2 = np.array(grid.convergence_f64())
-    np.savez(os.path.join(outdir, "rank%d.npz" % rank), fields=np.stack(fields), L0=L0, L1=L1, own_lo=own_lo, own_hi=own_hi, l2=l2)
+    rec = grid.receiver_data()
+    np.savez(os.path.join(outdir, "rank%d.npz" % rank), fields=np.stack(fields), L0=L0, L1=L1, own_lo=own_lo, own_hi=own_hi, l2=l2,
+             receivers=rec if rec is not None else np.zeros(0))
     grid.free()
     if use_cuda:
         lib.opesci_b200_comm_finalize()
