@@ -99,7 +99,7 @@ def main():
         fields.append(np.frombuffer(buf, dtype=np.float64 if p.is_double else np.float32).reshape(
             p.nlevels, L1 - L0, p.dim[1], p.dim[2]).copy())
     l2 = np.array(grid.convergence_f64())
-    rec = grid.receiver_data()
+    rec = grid.receiver_data() if hasattr(grid, 'receiver_data') else None
     np.savez(os.path.join(outdir, "rank%d.npz" % rank), fields=np.stack(fields), L0=L0, L1=L1, own_lo=own_lo, own_hi=own_hi, l2=l2,
              receivers=rec if rec is not None else np.zeros(0))
     grid.free()
