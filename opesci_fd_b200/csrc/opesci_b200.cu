@@ -362,6 +362,17 @@ void build_levander_hetero(Model &M)
             }
 }
 
+// number of SMs of the current device (148 on B200); grids are sized in multiples of it
+int sm_count()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 // ------------------------------------------------------------------ launch helpers
 struct Stepper {
     const Run &R;
@@ -402,7 +413,7 @@ struct Stepper {
         const Model &M = R.M;
         const int nx = M.G.dim[0] - 2 * M.m, ny = M.G.dim[1] - 2 * M.m, nz = M.G.dim[2] - 2 * M.m;
         const int nbz = (nz + K::TZ - 1) / K::TZ, nby = (ny + K::TY - 1) / K::TY;
-        int nchunks = (8 * 148 + nbz * nby - 1) / (nbz * nby);       // >= 8 CTAs per SM over the launch
+        int nchunks = (8 * sm_count() + nbz * nby - 1) / (nbz * nby);   // >= 8 CTAs per SM over the launch
         const int maxc = nx / (16 * M.m) > 0 ? nx / (16 * M.m) : 1;   // keep the 2m-plane warm-up of a chunk small
         if (nchunks > maxc) nchunks = maxc;
         if (nchunks < 1) nchunks = 1;
@@ -506,7 +517,7 @@ struct Stepper {
                     const Model &Md = R.M;
                     const int nx = Md.G.dim[0] - 2 * Md.m, ny = Md.G.dim[1] - 2 * Md.m;
                     const int nbz = (int)((Md.G.s[1] / 4 + 31) / 32), nby = (ny + 7) / 8;
-                    int nchunks = (8 * 148 + nbz * nby - 1) / (nbz * nby);   // >= 8 blocks per SM in flight
+                    int nchunks = (8 * sm_count() + nbz * nby - 1) / (nbz * nby);   // >= 8 blocks per SM in flight
                     if (nchunks < 1) nchunks = 1;
                     if (nchunks > nx / (4 * Md.m) && nx / (4 * Md.m) >= 1) nchunks = nx / (4 * Md.m);
                     const int xchunk = (nx + nchunks - 1) / nchunks;
@@ -868,8 +879,7 @@ int setup_fused(Run &R)
     else { if (set_fused_attr<2, OPESCI_ARITH_REFERENCE>() || set_fused_attr<2, OPESCI_ARITH_FAST>()) return 1; }
     // x-chunks: enough CTAs to fill the machine in whole waves, few enough to keep the 2m-plane
     // warm-up of every chunk negligible
-    int nsm = 148;
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+    const int nsm = sm_count();
     const int CZ = m == 1 ? FusedCfg<1>::CZ : FusedCfg<2>::CZ, CY = 16 - 2 * m;
     const long long tiles = (long long)((p.dim[2] - 2 * m + CZ - 1) / CZ) * ((p.dim[1] - 2 * m + CY - 1) / CY);
     const int nx = M.G.dim[0] - 2 * m;
