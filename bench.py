@@ -137,7 +137,10 @@ def run_reference_arm(args):
     value = statistics.median(samples)
     base["value"] = value
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Gpts/s", "n_gpus": args.gpus,
-            "steps": reps, "warmup": warm, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "steps": reps, "warmup": warm,
+            # time one time step of the named workload takes at the measured rate (the timed sample itself is 512^3)
+            "ms_per_step": float(args.n + 1) ** 3 * args.gpus / (value * 1e9) * 1e3,
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "eigenwave3d so=4 fp32 %d^3 (reference generated OpenMP C++ on host cores; "
                                    "bounded sample at 512^3)" % args.n},
