@@ -34,7 +34,7 @@ template <int M, typename T> struct TileCfg {
 #define OPESCI_TILED_MINB_F64 2
 #endif
 #ifndef OPESCI_TILED_MINB_F32
-#define OPESCI_TILED_MINB_F32 1
+#define OPESCI_TILED_MINB_F32 0   /* 0 = unspecified: the compiler keeps its own occupancy heuristic (so=8: 71 / 64 registers, 3-4 CTAs per SM) */
 #endif
     // resident CTAs per SM the register allocation must leave room for: the fp64 kernels otherwise take
     // 160+ registers (every window array live at once) and run with a single 8-warp CTA per SM
