@@ -247,13 +247,13 @@ int opesci_b200_release_host(void);
  * of all fields on each inner side, computes a whole time step on its local slab (x-face loops only
  * on the first / last rank) and then refreshes the halo planes by NCCL send/recv.  The host
  * distributes the 128-byte NCCL unique id (rank 0 creates it), e.g. with torch.distributed. */
-#define OPESCI_SLAB_HALO 8       /* >= 2m+3 for so=4: stress m, velocity m, Levander ghost chain 3 per step */
+#define OPESCI_SLAB_HALO 8       /* minimum halo; the halo is max(8, opesci_slab_need(kind, so)): 8 planes up to so=8, 2m beyond */
 #define OPESCI_COMM_ID_BYTES 128
 int opesci_b200_comm_unique_id(void *out_id, int nbytes);
 int opesci_b200_comm_init(int rank, int nranks, const void *id, int nbytes);
 int opesci_b200_comm_finalize(void);
 /* the planes [L0,L1) of global dim1 that rank `rank` of `nranks` stores (its slab plus halos): what a
- * heterogeneous run has to supply in rho/vp/vs (media_plane0 = L0, media_nplanes = L1-L0) */
+ * heterogeneous run has to supply in rho/vp/vs (media_plane0 = L0, media_nplanes = L1-L0); staggered elastic model */
 int opesci_b200_slab_range(int rank, int nranks, int gdim1, int so, int *L0, int *L1);
 /* 1 if this library was built with the CUDA kernels (0 for the CPU oracle build) */
 int opesci_b200_is_cuda(void);

@@ -24,10 +24,22 @@ typedef struct OpesciSlab {
     int lo_face, hi_face;
 } OpesciSlab;
 
-/* `need`: planes an error can travel inwards per step (2m+3 staggered elastic, m regular acoustic).
- * returns 0 on success, 1 if the slabs would be thinner than the halo or the halo is too thin */
-static inline int opesci_slab_make(OpesciSlab *s, int rank, int nranks, int gdim, int m, int halo, int need)
+/* Planes an error starting at an artificial slab end can travel inwards in one time step:
+ *   staggered elastic, Levander (so == 4):   stress m + velocity m + ghost-loop chain 3 = 2m+3
+ *   staggered elastic, Robertsson (so != 4): stress m + velocity m = 2m (its ghost loops only write zeros / in-axis mirrors)
+ *   regular acoustic:                        m                                                       */
+static inline int opesci_slab_need(int acoustic, int so)
 {
+    const int m = so / 2;
+    if (acoustic) return m;
+    return so == 4 ? 2 * m + 3 : 2 * m;
+}
+
+/* `need`: see opesci_slab_need; the halo is max(min_halo, need) planes per inner side.
+ * returns 0 on success, 1 if the slabs would be thinner than the halo */
+static inline int opesci_slab_make(OpesciSlab *s, int rank, int nranks, int gdim, int m, int min_halo, int need)
+{
+    const int halo = min_halo > need ? min_halo : need;
     if (nranks < 1) nranks = 1;
     const int n_int = gdim - 2 * m;
     const int base = n_int / nranks, rem = n_int % nranks;
@@ -40,7 +52,7 @@ static inline int opesci_slab_make(OpesciSlab *s, int rank, int nranks, int gdim
     s->own_hi = s->hi_face ? gdim : s->X1;
     s->L0 = s->lo_face ? 0 : s->X0 - halo;
     s->L1 = s->hi_face ? gdim : s->X1 + halo;
-    if (nranks > 1 && (base < halo || halo < need)) return 1;
+    if (nranks > 1 && base < halo) return 1;
     return 0;
 }
 

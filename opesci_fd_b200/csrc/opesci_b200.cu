@@ -1488,9 +1488,9 @@ int opesci_b200_configure(const OpesciB200Params *params)
     M.p = *params;
     M.m = params->so / 2;
     const int nranks = params->slab_nranks > 1 ? params->slab_nranks : 1;
-    const int need = params->kind == OPESCI_KIND_REGULAR_ACOUSTIC ? M.m : 2 * M.m + 3;   // include/opesci_slab.h
+    const int need = opesci_slab_need(params->kind == OPESCI_KIND_REGULAR_ACOUSTIC, params->so);   // include/opesci_slab.h
     if (opesci_slab_make(&M.slab, nranks > 1 ? params->slab_rank : 0, nranks, params->dim[0], M.m, OPESCI_SLAB_HALO, need))
-        return fail("opesci_b200_configure: slabs thinner than the halo (or so > 4 with slabs): use fewer ranks");
+        return fail("opesci_b200_configure: slabs thinner than the halo: use fewer ranks");
     if (nranks > 1 && (!g_nccl.comm || g_nccl.nranks != nranks || g_nccl.rank != params->slab_rank))
         return fail("opesci_b200_configure: slab_nranks > 1 needs opesci_b200_comm_init with the same rank / size first");
     for (int d = 0; d < 3; ++d) M.G.dim[d] = params->dim[d];
@@ -1712,7 +1712,7 @@ int opesci_b200_comm_init(int rank, int nranks, const void *id_bytes, int nbytes
 int opesci_b200_slab_range(int rank, int nranks, int gdim1, int so, int *L0, int *L1)
 {
     OpesciSlab sl;
-    if (opesci_slab_make(&sl, rank, nranks, gdim1, so / 2, OPESCI_SLAB_HALO, 0)) return fail("opesci_b200_slab_range: slabs thinner than the halo");
+    if (opesci_slab_make(&sl, rank, nranks, gdim1, so / 2, OPESCI_SLAB_HALO, opesci_slab_need(0, so))) return fail("opesci_b200_slab_range: slabs thinner than the halo");
     if (L0) *L0 = sl.L0;
     if (L1) *L1 = sl.L1;
     return 0;

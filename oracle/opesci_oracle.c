@@ -509,7 +509,7 @@ int opesci_b200_configure(const OpesciB200Params *params)
     M->gdim1 = params->dim[0];
     {
         const int nr = params->slab_nranks > 1 ? params->slab_nranks : 1;
-        const int need = params->kind == OPESCI_KIND_REGULAR_ACOUSTIC ? M->m : 2 * M->m + 3;
+        const int need = opesci_slab_need(params->kind == OPESCI_KIND_REGULAR_ACOUSTIC, params->so);
         if (opesci_slab_make(&M->slab, nr > 1 ? params->slab_rank : 0, nr, params->dim[0], M->m, OPESCI_SLAB_HALO, need))
             return fail("oracle: slabs thinner than the halo");
         if (nr > 1 && !g_exchange) return fail("oracle: slab_nranks > 1 needs opesci_oracle_set_exchange first");
@@ -668,7 +668,7 @@ int opesci_b200_comm_finalize(void) { return 0; }
 int opesci_b200_slab_range(int rank, int nranks, int gdim1, int so, int *L0, int *L1)
 {
     OpesciSlab sl;
-    if (opesci_slab_make(&sl, rank, nranks, gdim1, so / 2, OPESCI_SLAB_HALO, 0)) return fail("slabs thinner than the halo");
+    if (opesci_slab_make(&sl, rank, nranks, gdim1, so / 2, OPESCI_SLAB_HALO, opesci_slab_need(0, so))) return fail("slabs thinner than the halo");
     if (L0) *L0 = sl.L0;
     if (L1) *L1 = sl.L1;
     return 0;

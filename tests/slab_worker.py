@@ -82,7 +82,9 @@ def main():
     grid.run(library=lib)
     p = grid._params
     # local slab geometry (same arithmetic as include/opesci_slab.h)
-    m, H, gdim = p.so // 2, abi.SLAB_HALO, p.dim[0]
+    m, gdim = p.so // 2, p.dim[0]
+    need = m if p.kind == abi.KIND_REGULAR_ACOUSTIC else (2 * m + 3 if p.so == 4 else 2 * m)   # include/opesci_slab.h
+    H = max(abi.SLAB_HALO, need)
     n_int = gdim - 2 * m
     base, rem = divmod(n_int, world)
     X0 = m + rank * base + min(rank, rem)

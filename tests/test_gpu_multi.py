@@ -31,10 +31,11 @@ def _free_port():
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
-@pytest.mark.parametrize("arith,kind", [(abi.ARITH_REFERENCE, "eigenwave3d"), (abi.ARITH_FAST, "eigenwave3d"),
-                                        (abi.ARITH_REFERENCE, "eigenwave3d_read"), (abi.ARITH_REFERENCE, "simplewave3d")])
-def test_two_gpu_slabs_equal_single_gpu(arith, kind, cuda_lib, tmp_path):
-    cfg = dict(kind=kind, so=4, grid_size=[96, 70, 130], dt=0.002, steps=9, double=False,
+@pytest.mark.parametrize("arith,kind,so", [(abi.ARITH_REFERENCE, "eigenwave3d", 4), (abi.ARITH_FAST, "eigenwave3d", 4),
+                                           (abi.ARITH_REFERENCE, "eigenwave3d_read", 4), (abi.ARITH_REFERENCE, "simplewave3d", 4),
+                                           (abi.ARITH_REFERENCE, "eigenwave3d", 8), (abi.ARITH_REFERENCE, "eigenwave3d", 12)])
+def test_two_gpu_slabs_equal_single_gpu(arith, kind, so, cuda_lib, tmp_path):
+    cfg = dict(kind=kind, so=so, grid_size=[96, 70, 130], dt=0.002, steps=9, double=False,
                domain=[1.0, 0.9, 0.8], rho=1.2, vp=1.6, vs=0.8, seed=5)
     single = make_grid(cfg, flags=arith | abi.HOST_MIRROR_FULL)
     single.run(library=cuda_lib)

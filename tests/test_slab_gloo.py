@@ -25,7 +25,8 @@ def _free_port():
 
 
 @pytest.mark.parametrize("world,so,kind", [(2, 4, "eigenwave3d"), (3, 4, "eigenwave3d"), (2, 2, "eigenwave3d"),
-                                           (2, 4, "eigenwave3d_read"), (2, 4, "simplewave3d"), (3, 8, "simplewave3d")])
+                                           (2, 4, "eigenwave3d_read"), (2, 4, "simplewave3d"), (3, 8, "simplewave3d"),
+                                           (2, 8, "eigenwave3d"), (2, 12, "eigenwave3d"), (2, 6, "eigenwave3d_read")])
 def test_slab_decomposition_is_bit_exact(world, so, kind, oracle_lib, tmp_path):
     cfg = dict(kind=kind, so=so, grid_size=[30 * world, 11, 9], dt=0.002, steps=11, double=False,
                domain=[1.0 * world, 0.9, 0.8], rho=1.2, vp=1.6, vs=0.8, seed=11)
