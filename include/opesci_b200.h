@@ -247,7 +247,7 @@ int opesci_b200_release_host(void);
  * of all fields on each inner side, computes a whole time step on its local slab (x-face loops only
  * on the first / last rank) and then refreshes the halo planes by NCCL send/recv.  The host
  * distributes the 128-byte NCCL unique id (rank 0 creates it), e.g. with torch.distributed. */
-#define OPESCI_SLAB_HALO 8       /* minimum halo; the halo is max(8, opesci_slab_need(kind, so)): 8 planes up to so=8, 2m beyond */
+#define OPESCI_SLAB_HALO 8       /* minimum halo; the halo is max(8, need) with `need` from include/opesci_slab.h: 8 planes up to so=8, 2m beyond */
 #define OPESCI_COMM_ID_BYTES 128
 int opesci_b200_comm_unique_id(void *out_id, int nbytes);
 int opesci_b200_comm_init(int rank, int nranks, const void *id, int nbytes);
