@@ -104,6 +104,13 @@ EXPORTED_SYMBOLS = [
     "opesci_b200_comm_unique_id", "opesci_b200_comm_init", "opesci_b200_comm_finalize",
     "opesci_b200_reserve_host", "opesci_b200_release_host", "opesci_b200_slab_range",
 ]
+# include/opesci_io.h (model input / field output around the path)
+IO_SYMBOLS = [
+    "opesci_b200_set_output", "opesci_b200_output_stats", "opesci_b200_dump_field_vts_3d",
+    "opesci_b200_read_simple_binary_ptr", "opesci_b200_simple_binary_count", "opesci_b200_read_model_segy",
+    "opesci_b200_segy_decode_device", "opesci_b200_ibm_to_float", "opesci_b200_read_xyz",
+    "opesci_b200_resample_timeseries", "opesci_b200_calculate_dt", "opesci_b200_calculate_lame_constants",
+]
 SLAB_HALO = 8
 COMM_ID_BYTES = 128
 
@@ -148,6 +155,39 @@ def bind(lib):
         lib.opesci_b200_slab_range.restype = ctypes.c_int
     lib.opesci_b200_is_cuda.argtypes = []
     lib.opesci_b200_is_cuda.restype = ctypes.c_int
+    if hasattr(lib, "opesci_b200_set_output"):
+        bind_io(lib)
+    return lib
+
+
+def bind_io(lib):
+    """include/opesci_io.h"""
+    c_int, c_float, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+    PF, PI = POINTER(c_float), POINTER(c_int)
+    lib.opesci_b200_set_output.argtypes = [c_char_p, c_int, c_int]
+    lib.opesci_b200_set_output.restype = c_int
+    lib.opesci_b200_output_stats.argtypes = [PI, PI]
+    lib.opesci_b200_output_stats.restype = c_int
+    lib.opesci_b200_dump_field_vts_3d.argtypes = [c_char_p, PI, PF, c_int, PF, c_int]
+    lib.opesci_b200_dump_field_vts_3d.restype = c_int
+    lib.opesci_b200_read_simple_binary_ptr.argtypes = [c_char_p, PF, c_size_t]
+    lib.opesci_b200_read_simple_binary_ptr.restype = c_int
+    lib.opesci_b200_simple_binary_count.argtypes = [c_char_p]
+    lib.opesci_b200_simple_binary_count.restype = c_int64
+    lib.opesci_b200_read_model_segy.argtypes = [c_char_p, PF, c_size_t, PI, PF, c_int]
+    lib.opesci_b200_read_model_segy.restype = c_int
+    lib.opesci_b200_segy_decode_device.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
+    lib.opesci_b200_segy_decode_device.restype = c_int
+    lib.opesci_b200_ibm_to_float.argtypes = [POINTER(ctypes.c_ubyte), c_int]
+    lib.opesci_b200_ibm_to_float.restype = c_float
+    lib.opesci_b200_read_xyz.argtypes = [c_char_p, PF, c_int]
+    lib.opesci_b200_read_xyz.restype = c_int
+    lib.opesci_b200_resample_timeseries.argtypes = [PF, c_int, c_float, c_double, PF, c_int]
+    lib.opesci_b200_resample_timeseries.restype = c_int
+    lib.opesci_b200_calculate_dt.argtypes = [PF, c_size_t, c_float]
+    lib.opesci_b200_calculate_dt.restype = c_float
+    lib.opesci_b200_calculate_lame_constants.argtypes = [PF, PF, PF, c_size_t, PF, PF]
+    lib.opesci_b200_calculate_lame_constants.restype = None
     return lib
 
 

@@ -125,10 +125,13 @@ template <int M> struct FusedCfg {
 #ifndef OPESCI_FUSED_EZ
 #define OPESCI_FUSED_EZ 64
 #endif
+#ifndef OPESCI_FUSED_EY
+#define OPESCI_FUSED_EY 16
+#endif
 #ifndef OPESCI_FUSED_MINB
 #define OPESCI_FUSED_MINB 1
 #endif
-    static constexpr int EZ = OPESCI_FUSED_EZ, EY = 16;     // threads = stress tile (incl. recomputed halo)
+    static constexpr int EZ = OPESCI_FUSED_EZ, EY = OPESCI_FUSED_EY;     // threads = stress tile (incl. recomputed halo)
     // stored tile.  TMA needs the innermost box coordinate 16-B aligned (measured on B200: an
     // unaligned start raises "illegal instruction"), so tiles advance in multiples of 4 floats
     // along z and the box starts OFFZ >= M floats left of the stress tile.

@@ -11,6 +11,7 @@
 // There is no CPU fallback: every entry point fails loudly without a CUDA device.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -25,6 +26,7 @@
 #include "../../include/opesci_slab.h"
 #include "fused.cuh"
 #include "hetero.cuh"
+#include "io.cuh"
 #include "kernels.cuh"
 #include "tiled.cuh"
 
@@ -864,14 +866,17 @@ int setup_fused(Run &R)
     EncodeTiledFn encode = get_encode();
     if (!encode) return fail("cuTensorMapEncodeTiled not available from the driver");
     const int m = M.m;
-    const int VZ = m == 1 ? FusedCfg<1>::VZ : FusedCfg<2>::VZ, VY = 16 + 2 * m;
+    const int VZ = m == 1 ? FusedCfg<1>::VZ : FusedCfg<2>::VZ, VY = OPESCI_FUSED_EY + 2 * m;
     for (int f = 0; f < 3; ++f) {
         cuuint64_t gdim[3] = {(cuuint64_t)p.dim[2], (cuuint64_t)p.dim[1], (cuuint64_t)M.G.dim[0] * p.nlevels};
         cuuint64_t gstride[2] = {(cuuint64_t)M.G.s[1] * 4, (cuuint64_t)M.G.s[0] * 4};
         cuuint32_t box[3] = {(cuuint32_t)VZ, (cuuint32_t)VY, 1};
         cuuint32_t estr[3] = {1, 1, 1};
+#ifndef OPESCI_FUSED_L2PROMO
+#define OPESCI_FUSED_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+#endif
         CUresult rc = encode(&R.tmap[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, R.dev[f], gdim, gstride, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, OPESCI_FUSED_L2PROMO,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rc != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed");
     }
@@ -880,7 +885,7 @@ int setup_fused(Run &R)
     // x-chunks: enough CTAs to fill the machine in whole waves, few enough to keep the 2m-plane
     // warm-up of every chunk negligible
     const int nsm = sm_count();
-    const int CZ = m == 1 ? FusedCfg<1>::CZ : FusedCfg<2>::CZ, CY = 16 - 2 * m;
+    const int CZ = m == 1 ? FusedCfg<1>::CZ : FusedCfg<2>::CZ, CY = OPESCI_FUSED_EY - 2 * m;
     const long long tiles = (long long)((p.dim[2] - 2 * m + CZ - 1) / CZ) * ((p.dim[1] - 2 * m + CY - 1) / CY);
     const int nx = M.G.dim[0] - 2 * m;
     double best = -1.0;
@@ -891,6 +896,9 @@ int setup_fused(Run &R)
         const double eff = waves / (double)((long long)(waves + 0.999999)) * len / (len + 2.0 * m + 2.0);
         if (eff > best) { best = eff; R.nchunks = nc; }
     }
+#ifdef OPESCI_FUSED_NCHUNKS
+    R.nchunks = OPESCI_FUSED_NCHUNKS;   // A/B experiments (tools/ab.py)
+#endif
     auto uniform = [&](int lo, int hi, int nc, int first) {   // chunks first .. first+nc-1 cover [lo, hi)
         const int len = (hi - lo + nc - 1) / nc;
         for (int c = 0; c <= nc; ++c) R.xs[first + c] = lo + c * len < hi ? lo + c * len : hi;
@@ -926,7 +934,7 @@ int setup_fused(Run &R)
         const int nc = nx >= 8 * 96 ? 8 : 6;
         R.nchunks = nc;
         uniform(m, M.G.dim[0] - m, nc, 0);
-        const int EY = 16, EZ = OPESCI_FUSED_EZ;
+        const int EY = OPESCI_FUSED_EY, EZ = OPESCI_FUSED_EZ;
         const int dims[3] = {M.G.dim[1], M.G.dim[2], M.G.dim[0]};
         const int ntile[3] = {(p.dim[1] - 2 * m + CY - 1) / CY, (p.dim[2] - 2 * m + CZ - 1) / CZ, nc};
         for (int a = 0; a < 3; ++a) {
@@ -1002,6 +1010,17 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     CUDA_OK(cudaStreamSynchronize(st));
     if (S.err != cudaSuccess) return fail("kernel launch failed during initialisation: %s", cudaGetErrorString(S.err));
 
+    // per-step field output (include/opesci_io.h: opesci_b200_set_output; reference regulargrid.py:702-719)
+    opesci_io::Snapshotter snap;
+    if (opesci_io::output_cfg().armed) {
+        if (opesci_io::output_cfg().field >= p.nfields) return fail("opesci_b200_set_output: no such field");
+        const int ldims[3] = {M.G.dim[0], p.dim[1], p.dim[2]};
+        const int own_lo = slabs ? M.slab.X0 - M.slab.L0 : 0, own_hi = slabs ? M.slab.X1 - M.slab.L0 : M.G.dim[0];
+        const char *e = snap.init(R.dev[opesci_io::output_cfg().field], sizeof(T), (size_t)M.G.level, (size_t)M.G.s[1], ldims, own_lo, own_hi,
+                                  slabs ? M.slab.X0 : 0, p.dx, M.slab.rank, slabs ? M.slab.nranks : 1);
+        if (e) return fail("%s", e);
+    }
+#define SNAP_OK(call) do { const char *e_ = (call); if (e_) return fail("%s", e_); } while (0)
     cudaEvent_t e0, e1;
     CUDA_OK(cudaEventCreate(&e0));
     CUDA_OK(cudaEventCreate(&e1));
@@ -1013,7 +1032,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     cudaGraphExec_t gexec = nullptr;
     cudaStream_t st2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    const bool pipelined = staggered && R.fused && R.overlap && !slabs;
+    const bool pipelined = staggered && R.fused && R.overlap && !slabs && !snap.armed;
     if (pipelined) {
         // ---- software-pipelined stepping: the ghost loops + shell update of step n-1 (latency-bound, they
         // leave most of the machine idle) run on a second stream concurrently with the tiles of step n that
@@ -1091,6 +1110,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
         bool pending = false;
         auto step = [&](int ti) -> int {
             const int t0 = ti % 2, t1 = (t0 + 1) % 2;
+            SNAP_OK(snap.before_step(st, ti));
             S.template fused<SO, T, ARITH>(t0, t1, 0, R.mid0, R.mid1 - R.mid0);
             if (pending) { CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0)); pending = false; }
             S.template fused<SO, T, ARITH>(t0, t1, 0, 0, R.mid0);
@@ -1099,6 +1119,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
             S.template velocity_shell<SO, T, ARITH>(t0, t1);
             S.template velocity_bc<T>(t1);
             S.template point_hooks<T>(t1);
+            SNAP_OK(snap.after_step(st, ti, t1));   // owned planes only: they are final before the halo exchange
             CUDA_OK(cudaEventRecord(ev_fork, st));
             CUDA_OK(cudaStreamWaitEvent(st2, ev_fork, 0));
             if (exchange(t1, st2)) return 1;
@@ -1122,7 +1143,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
         CUDA_OK(cudaStreamSynchronize(st));
         CUDA_OK(cudaStreamSynchronize(st2));
     } else {
-    const bool use_graph = !(p.flags & OPESCI_NO_CUDA_GRAPH) && nsteps >= 2 * period && !slabs;
+    const bool use_graph = !(p.flags & OPESCI_NO_CUDA_GRAPH) && nsteps >= 2 * period && !slabs && !snap.armed;
     if (use_graph) {
         // one period of steps (time-level indices repeat with it) captured once, replayed
         CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -1144,9 +1165,11 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
                 S.launches += per_period;
                 ti += period;
             } else {
+                SNAP_OK(snap.before_step(st, ti));
                 if (staggered) S.template staggered_step<SO, T, ARITH>(ti);
                 else S.template acoustic_step<SO, T, ARITH>(ti);
                 // the level this step wrote: t1 = (ti+1)%2 (staggered), t2 = (ti+2)%3 (regular)
+                SNAP_OK(snap.after_step(st, ti, staggered ? (ti + 1) % 2 : (ti + 2) % 3));
                 if (slabs && exchange(staggered ? (ti + 1) % 2 : (ti + 2) % 3, st)) return 1;
                 ++ti;
             }
@@ -1162,6 +1185,8 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     CUDA_OK(cudaEventRecord(e1, st));
     }
     CUDA_OK(cudaStreamSynchronize(st));
+    snap.finish();
+    if (opesci_io::write_errors().load() > 0) return fail("per-step field output: writing a .vts file failed");
     if (S.err != cudaSuccess) return fail("kernel launch failed in the time loop: %s", cudaGetErrorString(S.err));
     CUDA_OK(cudaGetLastError());
     float ms = 0.f;

@@ -151,7 +151,19 @@ class Grid(object):
             raise RuntimeError("opesci_b200_configure: %s" % lib.opesci_b200_last_error().decode())
         self._arg_grid = abi.OpesciGrid()
         self._arg_profiling = abi.OpesciProfiling()
-        if lib.opesci_execute(byref(self._arg_grid), byref(self._arg_profiling)) != 0:
+        # `output_vts` switch: the generator emits a per-step dump of the first field into "<label>_<ti>.vts"
+        # (reference: opesci/regulargrid.py:702-719, staggeredgrid.py:882-890); here the library streams it
+        # out asynchronously (include/opesci_io.h)
+        armed = bool(getattr(self, "output_vts", False)) and hasattr(lib, "opesci_b200_set_output")
+        if armed:
+            prefix = "%s%s_" % (getattr(self, "output_prefix", ""), str(self.fields[0].label))
+            lib.opesci_b200_set_output(prefix.encode(), 0, int(getattr(self, "output_every", 1)))
+        try:
+            rc = lib.opesci_execute(byref(self._arg_grid), byref(self._arg_profiling))
+        finally:
+            if armed:
+                lib.opesci_b200_set_output(None, 0, 0)
+        if rc != 0:
             self._arg_grid = None
             raise RuntimeError("opesci_execute: %s" % lib.opesci_b200_last_error().decode())
         return self._arg_grid

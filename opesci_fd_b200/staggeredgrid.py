@@ -188,7 +188,10 @@ class StaggeredGrid(RegularGrid):
             n = dims[0] * dims[1] * dims[2]
             arrs = []
             for fn in (self.rho_file, self.vp_file, self.vs_file):
-                a = np.fromfile(fn, dtype='<f4', count=n)     # opesciIO.cpp:319: flat float32
+                if str(fn).lower().endswith(('.segy', '.sgy')):
+                    a = self._read_segy(fn, dims)              # opesciIO.cpp:451-612: SEG-Y model volume
+                else:
+                    a = np.fromfile(fn, dtype='<f4', count=n)     # opesciIO.cpp:319: flat float32
                 if a.size != n:
                     raise IOError("%s: expected %d float32 values, found %d" % (fn, n, a.size))
                 arrs.append(np.ascontiguousarray(a.reshape(dims), dtype=np.float32))
@@ -197,6 +200,25 @@ class StaggeredGrid(RegularGrid):
             if a.ndim != 3 or list(a.shape[1:]) != dims[1:]:
                 raise ValueError("media arrays must be [nplanes][dim2][dim3] = [*][%d][%d]" % (dims[1], dims[2]))
         return self.media_arrays
+
+    def _read_segy(self, filename, dims):
+        """SEG-Y model volume (IBM floats) through the library's reader (include/opesci_io.h), already in the
+        [x][y][z] layout of rho / vp / vs; the volume must cover the whole array including the ghost planes,
+        like the raw files the reference reads (vsize = dim1*dim2*dim3, staggeredgrid.py:549-551)."""
+        import ctypes
+        if self._library is None:
+            self._load_library()
+        lib = self._library
+        dim = (ctypes.c_int * 3)()
+        sp = (ctypes.c_float * 3)()
+        if lib.opesci_b200_read_model_segy(str(filename).encode(), None, 0, dim, sp, 1) != 0:
+            raise IOError("%s: not a readable SEG-Y model volume (format code 1)" % filename)
+        if list(dim) != list(dims):
+            raise IOError("%s: SEG-Y volume is %s, the grid needs %s" % (filename, list(dim), list(dims)))
+        a = np.zeros(dims[0] * dims[1] * dims[2], dtype=np.float32)
+        if lib.opesci_b200_read_model_segy(str(filename).encode(), a.ctypes.data_as(abi.POINTER(abi.c_float)), a.size, dim, sp, 1) != 0:
+            raise IOError("%s: SEG-Y read failed" % filename)
+        return a
 
     # ------------------------------------------------------------------ point source + receivers
     def _cell_of(self, coord):

@@ -193,7 +193,7 @@ converge:  Convergence test of the (2,4) scheme, which is 2nd order
     p.add_argument('-x', '--execute', action='store_true', default=False,
                    help='Dynamically execute the model on the GPU')
     p.add_argument('-n', '--nthreads', type=int, default=1, help='Number of host threads (unused on GPU)')
-    p.add_argument('-o', '--output', action='store_true', default=False, help='(accepted, ignored) .vts output')
+    p.add_argument('-o', '--output', action='store_true', default=False, help='write U_<ti>.vts after every time step (output_vts switch)')
     p.add_argument('-p', '--profiling', action='store_true', default=False,
                    help='Print time-loop timing from CUDA events')
     p.add_argument('--papi-events', dest='papi_events', nargs='+', default=[], help='(accepted, ignored)')
@@ -207,11 +207,11 @@ converge:  Convergence test of the (2,4) scheme, which is 2nd order
     print("Eigenwave3D example (mode=%s)" % args.mode)
 
     if args.mode == 'default':
-        default(compiler=args.compiler, execute=args.execute, nthreads=args.nthreads, output=False,
+        default(compiler=args.compiler, execute=args.execute, nthreads=args.nthreads, output=args.output,
                 accuracy_order=[2, args.so, args.so, args.so], profiling=args.profiling,
                 double=args.double)
     elif args.mode == 'read':
-        read_data(compiler=args.compiler, execute=args.execute, nthreads=args.nthreads,
+        read_data(compiler=args.compiler, execute=args.execute, nthreads=args.nthreads, output=args.output,
                   accuracy_order=[2, args.so, args.so, args.so], profiling=args.profiling, synthetic=args.synthetic)
     elif args.mode == 'converge':
         converge_test()
