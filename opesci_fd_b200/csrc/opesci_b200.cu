@@ -1015,9 +1015,10 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     if (opesci_io::output_cfg().armed) {
         if (opesci_io::output_cfg().field >= p.nfields) return fail("opesci_b200_set_output: no such field");
         const int ldims[3] = {M.G.dim[0], p.dim[1], p.dim[2]};
-        const int own_lo = slabs ? M.slab.X0 - M.slab.L0 : 0, own_hi = slabs ? M.slab.X1 - M.slab.L0 : M.G.dim[0];
+        // slabs: the planes this rank owns, physical ghost planes of the end ranks included -- the pieces tile the array
+        const int own_lo = slabs ? M.slab.own_lo - M.slab.L0 : 0, own_hi = slabs ? M.slab.own_hi - M.slab.L0 : M.G.dim[0];
         const char *e = snap.init(R.dev[opesci_io::output_cfg().field], sizeof(T), (size_t)M.G.level, (size_t)M.G.s[1], ldims, own_lo, own_hi,
-                                  slabs ? M.slab.X0 : 0, p.dx, M.slab.rank, slabs ? M.slab.nranks : 1);
+                                  slabs ? M.slab.own_lo : 0, p.dx, M.slab.rank, slabs ? M.slab.nranks : 1);
         if (e) return fail("%s", e);
     }
 #define SNAP_OK(call) do { const char *e_ = (call); if (e_) return fail("%s", e_); } while (0)

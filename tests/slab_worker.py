@@ -79,7 +79,11 @@ def main():
         p.slab_rank, p.slab_nranks = rank, world
         return p, keep
     grid.build_params = with_slab
+    if cfg.get("vts_prefix") and use_cuda:
+        lib.opesci_b200_set_output(cfg["vts_prefix"].encode(), 0, cfg.get("vts_every", 1))
     grid.run(library=lib)
+    if cfg.get("vts_prefix") and use_cuda:
+        lib.opesci_b200_set_output(None, 0, 0)
     p = grid._params
     # local slab geometry (same arithmetic as include/opesci_slab.h)
     m, gdim = p.so // 2, p.dim[0]

@@ -59,3 +59,29 @@ def test_two_gpu_slabs_equal_single_gpu(arith, kind, so, cuda_lib, tmp_path):
         # every rank holds the all-reduced global norms
         np.testing.assert_allclose(z["l2"], ref_l2, rtol=1e-12)
     assert covered == ref.shape[2]
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
+@pytest.mark.parametrize("so", [4, 8])
+def test_two_gpu_vts_pieces_tile_the_single_gpu_snapshot(so, cuda_lib, tmp_path):
+    """per-step field output with slabs: every rank writes the planes it owns; together they are the single-GPU file"""
+    from test_io import read_vts
+    cfg = dict(kind="eigenwave3d", so=so, grid_size=[96, 30, 34], dt=0.002, steps=4, double=False, domain=[1.0, 0.9, 0.8])
+    one = str(tmp_path / "one_")
+    cuda_lib.opesci_b200_set_output(one.encode(), 0, 2)
+    single = make_grid(cfg, flags=abi.ARITH_REFERENCE | abi.HOST_MIRROR_NONE)
+    single.run(library=cuda_lib)
+    single.free()
+    cuda_lib.opesci_b200_set_output(None, 0, 0)
+    os.environ["OPESCI_TEST_FLAGS"] = str(abi.ARITH_REFERENCE | abi.HOST_MIRROR_FULL)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "slab_worker.py"), str(tmp_path), json.dumps(dict(cfg, vts_prefix=str(tmp_path / "two_"), vts_every=2)), "cuda"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    for ti in (0, 2):
+        _, f1, p1 = read_vts("%s%d.vts" % (one, ti))
+        parts = [read_vts("%s%d_r%d.vts" % (str(tmp_path / "two_"), ti, r)) for r in range(2)]
+        f2 = np.concatenate([p[1] for p in parts])
+        p2 = np.concatenate([p[2] for p in parts])
+        assert np.array_equal(f1.view(np.uint32), f2.view(np.uint32)) and np.array_equal(p1, p2)
