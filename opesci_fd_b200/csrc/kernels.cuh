@@ -384,7 +384,15 @@ struct FaceBatch {
 // 128-thread blocks with few registers: these loops are meant to run NEXT TO a resident fused_step CTA
 // (512 threads x 112 registers leave 8192 registers per SM), see the pipelined stepping in opesci_b200.cu
 #define OPESCI_FACE_THREADS 128
-template <typename T>
+// Cells per thread along the second free axis in homogeneous mode: the term table of a loop (field, level, offset,
+// literal) is decoded once and applied to CPT cells, and CPT x nterm independent loads are in flight per thread.
+// The loops on the contiguous x / y faces were instruction-bound (ncu: ~50 % issue slots at 5 % DRAM), not memory-bound.
+#ifndef OPESCI_FACE_CPT
+#define OPESCI_FACE_CPT 2
+#endif
+// HET = false drops the media operands, the shared denominator and the double-typed terms of the heterogeneous
+// Levander forms from the instantiation (80 -> fewer registers, twice the resident warps).
+template <typename T, bool HET, int CPT>
 __global__ void __launch_bounds__(OPESCI_FACE_THREADS)
 face_batch(const __grid_constant__ FieldPtrs F, const __grid_constant__ GridGeom G, const __grid_constant__ FaceBatch B,
            const __grid_constant__ MediaPtrs MD)
@@ -399,79 +407,118 @@ face_batch(const __grid_constant__ FieldPtrs F, const __grid_constant__ GridGeom
     const int e1 = (d == 0) ? 1 : 0, e2 = (d == 2) ? 1 : 2;
     // threads run along e2 (contiguous z) except on z-faces, where 8 x 32 tiles keep a little locality
     const int w = (d == 2) ? 8 : 128, h = OPESCI_FACE_THREADS / w;
-    const int j = L.lo + bx * w + (int)(threadIdx.x % w);
+    const int j0 = L.lo + bx * (w * CPT) + (int)(threadIdx.x % w);   // cells j0 + c*w, c < CPT
     const int i = L.lo1 + by * h + (int)(threadIdx.x / w);
-    if (i >= L.hi1 || j >= L.hi2) return;
-    const long long q = (long long)i * G.s[e1] + (long long)j * G.s[e2];
+    if (i >= L.hi1 || j0 >= L.hi2) return;
+    bool live[CPT];
+    long long q[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        live[c] = j0 + c * w < L.hi2;
+        q[c] = (long long)i * G.s[e1] + (long long)(live[c] ? j0 + c * w : j0) * G.s[e2];
+    }
     if (L.kind == 0) {
         T *A = (T *)F.f[L.field] + (long long)L.level * G.level;
         for (int k = 0; k < L.ops.count; ++k) {
-            const T v = L.ops.src[k] < 0 ? (T)0 : -A[q + (long long)L.ops.src[k] * G.s[d]];
-            A[q + (long long)L.ops.dst[k] * G.s[d]] = v;
+            const long long so_ = (long long)L.ops.src[k] * G.s[d], do_ = (long long)L.ops.dst[k] * G.s[d];
+            T v[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) v[c] = L.ops.src[k] < 0 ? (T)0 : -A[q[c] + so_];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c)
+                if (live[c]) A[q[c] + do_] = v[c];
         }
     } else {
-        const long long p = q + (long long)L.n * G.s[d];
+        const long long pn = (long long)L.n * G.s[d];
         const long long lv[2] = {(long long)L.lv0 * G.level, (long long)L.lv1 * G.level};
         // Phase 1: issue every operand load of the sum before any arithmetic.  The sum itself is a serial
         // chain (reference order); with the loads inside that chain every term would cost a full memory
         // latency (measured: these loops were latency-bound at ~14 dependent loads per cell).
         const int nt = L.eq.nterm;
-        const bool het = L.eq.da != 0.f || L.eq.db != 0.f || L.eq.term[nt - 1].mk != MK_NONE || L.eq.term[0].mk != MK_NONE;
-        T g[OPESCI_MAX_FACE_TERMS];
-        float ma[OPESCI_MAX_FACE_TERMS], mb[OPESCI_MAX_FACE_TERMS];
+        const bool het = HET && (L.eq.da != 0.f || L.eq.db != 0.f || L.eq.term[nt - 1].mk != MK_NONE || L.eq.term[0].mk != MK_NONE);
+        T g[CPT][OPESCI_MAX_FACE_TERMS];
+        float ma[HET ? CPT : 1][HET ? OPESCI_MAX_FACE_TERMS : 1], mb[HET ? CPT : 1][HET ? OPESCI_MAX_FACE_TERMS : 1];
 #pragma unroll
         for (int k = 0; k < OPESCI_MAX_FACE_TERMS; ++k) {
-            g[k] = 0;
-            ma[k] = mb[k] = 0.f;
             if (k < nt) {
                 const DevTerm &t = L.eq.term[k];
-                g[k] = ((const T *)F.f[t.field])[lv[t.level] + p + t.off];
-                if (het && t.mk != MK_NONE) {
-                    ma[k] = MD.m[t.ma][p + t.moffa];
-                    mb[k] = MD.m[t.mb][p + t.moffb];
+                const T *src = (const T *)F.f[t.field] + lv[t.level] + pn + t.off;
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) g[c][k] = src[q[c]];
+                if constexpr (HET) {
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) {
+                        ma[c][k] = mb[c][k] = 0.f;
+                        if (het && t.mk != MK_NONE) {
+                            ma[c][k] = MD.m[t.ma][q[c] + pn + t.moffa];
+                            mb[c][k] = MD.m[t.mb][q[c] + pn + t.moffb];
+                        }
+                    }
                 }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) g[c][k] = 0;
             }
         }
         // heterogeneous Levander loops: every `/D` term of one equation shares D = da*lambda + db*mu
-        float D = 0.f;
-        if (L.eq.da != 0.f || L.eq.db != 0.f)
-            D = __fadd_rn(__fmul_rn(L.eq.da, MD.m[OPESCI_MEDIA_LAMBDA][p + L.eq.doff]),
-                          __fmul_rn(L.eq.db, MD.m[OPESCI_MEDIA_MU][p + L.eq.doff]));
+        float D[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            D[c] = 0.f;
+            if constexpr (HET)
+                if (L.eq.da != 0.f || L.eq.db != 0.f)
+                    D[c] = __fadd_rn(__fmul_rn(L.eq.da, MD.m[OPESCI_MEDIA_LAMBDA][q[c] + pn + L.eq.doff]),
+                                     __fmul_rn(L.eq.db, MD.m[OPESCI_MEDIA_MU][q[c] + pn + L.eq.doff]));
+        }
         // Phase 2: the emitted sum, term by term
-        T acc = 0;
-        double accd = 0.0;   // the running sum once a double-typed term (pow(mu,2)) has been met
-        bool first = true, wide = false;
+        T acc[CPT];
+        double accd[CPT];   // the running sum once a double-typed term (pow(mu,2)) has been met
+        bool wide = false;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) { acc[c] = 0; accd[c] = 0.0; }
+        bool first = true;
 #pragma unroll
         for (int k = 0; k < OPESCI_MAX_FACE_TERMS; ++k) {
             if (k < nt) {
                 const DevTerm &t = L.eq.term[k];
-                T v = t.kind == TERM_MUL ? mul_rn<T>((T)t.coef, g[k]) : g[k];
-                if (t.mk == MK_SQ_DIV) {
-                    // `pow(mu,2)` is double in the emitted C++: the term, and from it on the running sum, are double
-                    double vd = __ddiv_rn(__dmul_rn((double)v, __dmul_rn((double)mb[k], (double)mb[k])), (double)D);
-                    if (t.kind == TERM_MINUS) vd = -vd;
-                    accd = first ? vd : __dadd_rn(wide ? accd : (double)acc, vd);
-                    wide = true;
-                } else {
-                    if (t.mk != MK_NONE) {
-                        // heterogeneous terms: fp32 only, the reference's left-to-right evaluation
-                        const float A = ma[k], Bm = mb[k];
-                        float w = (float)v;
-                        if (t.mk == MK_A) w = __fmul_rn(w, A);
-                        else if (t.mk == MK_A_DIV) w = __fdiv_rn(__fmul_rn(w, A), D);
-                        else if (t.mk == MK_AB_DIV) w = __fdiv_rn(__fmul_rn(__fmul_rn(w, A), Bm), D);
-                        else w = __fdiv_rn(__fmul_rn(w, A), Bm);
-                        v = (T)w;
+                const bool sq = HET && t.mk == MK_SQ_DIV;
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    T v = t.kind == TERM_MUL ? mul_rn<T>((T)t.coef, g[c][k]) : g[c][k];
+                    if (sq) {
+                        if constexpr (HET) {
+                            // `pow(mu,2)` is double in the emitted C++: the term, and from it on the running sum, are double
+                            double vd = __ddiv_rn(__dmul_rn((double)v, __dmul_rn((double)mb[c][k], (double)mb[c][k])), (double)D[c]);
+                            if (t.kind == TERM_MINUS) vd = -vd;
+                            accd[c] = first ? vd : __dadd_rn(wide ? accd[c] : (double)acc[c], vd);
+                        }
+                    } else {
+                        if constexpr (HET) {
+                            if (t.mk != MK_NONE) {
+                                // heterogeneous terms: fp32 only, the reference's left-to-right evaluation
+                                const float A = ma[c][k], Bm = mb[c][k];
+                                float wv = (float)v;
+                                if (t.mk == MK_A) wv = __fmul_rn(wv, A);
+                                else if (t.mk == MK_A_DIV) wv = __fdiv_rn(__fmul_rn(wv, A), D[c]);
+                                else if (t.mk == MK_AB_DIV) wv = __fdiv_rn(__fmul_rn(__fmul_rn(wv, A), Bm), D[c]);
+                                else wv = __fdiv_rn(__fmul_rn(wv, A), Bm);
+                                v = (T)wv;
+                            }
+                        }
+                        if (t.kind == TERM_MINUS) v = -v;
+                        if (first) acc[c] = v;
+                        else if (HET && wide) accd[c] = __dadd_rn(accd[c], (double)v);
+                        else acc[c] = add_rn<T>(acc[c], v);
                     }
-                    if (t.kind == TERM_MINUS) v = -v;
-                    if (first) acc = v;
-                    else if (wide) accd = __dadd_rn(accd, (double)v);
-                    else acc = add_rn<T>(acc, v);
                 }
+                if (sq) wide = true;
                 first = false;
             }
         }
-        ((T *)F.f[L.eq.out])[lv[L.eq.out_level] + p] = wide ? (T)accd : acc;
+        T *dst = (T *)F.f[L.eq.out] + lv[L.eq.out_level] + pn;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c)
+            if (live[c]) dst[q[c]] = (HET && wide) ? (T)accd[c] : acc[c];
     }
 }
 

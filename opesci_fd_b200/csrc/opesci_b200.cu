@@ -538,16 +538,19 @@ struct Stepper {
     {
         if (B.count == 0) return;
         const Model &M = R.M;
+        const bool het = M.p.hetero != 0;
+        const int cpt = het ? 1 : OPESCI_FACE_CPT;
         int total = 0;
         for (int k = 0; k < B.count; ++k) {
             const FaceLoop &L = B.loop[k];
-            const int w = L.d == 2 ? 8 : 128, h = OPESCI_FACE_THREADS / w;
+            const int w = (L.d == 2 ? 8 : 128) * cpt, h = OPESCI_FACE_THREADS / (L.d == 2 ? 8 : 128);
             B.nbx[k] = (L.hi2 - L.lo + w - 1) / w;
             B.start[k] = total;
             total += B.nbx[k] * ((L.hi1 - L.lo1 + h - 1) / h);
         }
         B.start[B.count] = total;
-        face_batch<T><<<total, OPESCI_FACE_THREADS, 0, st>>>(ptrs(), M.G, B, media());
+        if (het) face_batch<T, true, 1><<<total, OPESCI_FACE_THREADS, 0, st>>>(ptrs(), M.G, B, media());
+        else face_batch<T, false, OPESCI_FACE_CPT><<<total, OPESCI_FACE_THREADS, 0, st>>>(ptrs(), M.G, B, media());
         check();
     }
     // loop ranges of one ghost loop: the reference uses [lo, dim - himargin) on both free axes

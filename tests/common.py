@@ -12,7 +12,8 @@ FIELD_ORDER = ["U", "V", "W", "Txx", "Tyy", "Tzz", "Txy", "Tyz", "Txz"]
 
 
 def golden_names(prefix=""):
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith(prefix))
+    # io_*.npz are the vectors of include/opesci_io.h (tests/test_io.py), not field fixtures
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith(prefix) and not f.startswith("io_"))
 
 
 def load_golden(name):
