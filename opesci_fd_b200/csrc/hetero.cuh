@@ -104,12 +104,12 @@ __device__ __forceinline__ void window_ref_h(float &acc, bool &first, const floa
 
 template <int SO, int ARITH>
 __global__ void __launch_bounds__(256)
-stress_interior_h(FieldPtrs F, MediaPtrs MD, GridGeom G, HeteroCoefs C, int t0, int t1)
+stress_interior_h(FieldPtrs F, MediaPtrs MD, GridGeom G, HeteroCoefs C, int t0, int t1, int x0 = SO / 2, int z0 = SO / 2)
 {
     constexpr int M = SO / 2;
-    const int z = M + blockIdx.x * blockDim.x + threadIdx.x;
+    const int z = z0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int y = M + blockIdx.y * blockDim.y + threadIdx.y;
-    const int x = M + blockIdx.z;
+    const int x = x0 + blockIdx.z;
     if (z >= G.dim[2] - M || y >= G.dim[1] - M) return;
     const long long p = (long long)x * G.s[0] + (long long)y * G.s[1] + z;
     const long long r = (long long)t0 * G.level + p, w = (long long)t1 * G.level + p;

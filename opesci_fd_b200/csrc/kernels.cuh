@@ -110,12 +110,14 @@ __device__ __forceinline__ T window_fast(const T *__restrict__ g, long long stri
 // regardless of staggering (regulargrid.py:573-578).
 template <int SO, typename T, int ARITH>
 __global__ void __launch_bounds__(256)
-stress_interior(FieldPtrs F, GridGeom G, StaggeredCoefs C, int t0, int t1)
+stress_interior(FieldPtrs F, GridGeom G, StaggeredCoefs C, int t0, int t1, int x0 = SO / 2, int z0 = SO / 2)
 {
     constexpr int M = SO / 2;
-    const int z = M + blockIdx.x * blockDim.x + threadIdx.x;
+    // (x0, z0): first plane / first z column of the launch (the whole interior by default; the z strip next to the
+    // last full tile of the fused kernel otherwise, opesci_b200.cu:fused)
+    const int z = z0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int y = M + blockIdx.y * blockDim.y + threadIdx.y;
-    const int x = M + blockIdx.z;
+    const int x = x0 + blockIdx.z;
     if (z >= G.dim[2] - M || y >= G.dim[1] - M) return;
     const long long p = (long long)x * G.s[0] + (long long)y * G.s[1] + z;
     const long long r = (long long)t0 * G.level + p, w = (long long)t1 * G.level + p;

@@ -143,6 +143,7 @@ struct Run {
     CUtensorMap tmap9[OPESCI_MAX_FIELDS];   // all nine fields, box = TileCfg tile
     int nchunks = 1;                // x-chunks of the fused kernel: chunk c covers planes [xs[c], xs[c+1])
     int xs[OPESCI_MAX_CHUNKS + 1] = {};
+    int zstrip = 0;                 // > 0: the fused kernel covers z < zstrip only; the thin strip [zstrip, dim-m) is done per point
     int mid0 = 0, mid1 = 0;         // slabs: chunks [mid0, mid1) read no halo plane (they overlap the halo exchange)
     bool overlap = false;           // ghost loops of step n-1 run concurrently with the independent tiles of step n
     int box_lo[3] = {0, 0, 0}, box_hi[3] = {0, 0, 0};   // independent tiles (tile_y, tile_z, chunk)
@@ -726,10 +727,23 @@ struct Stepper {
             if (count <= 0) return;
             A.mode = mode;
             for (int k = 0; k < 3; ++k) { A.box_lo[k] = R.box_lo[k]; A.box_hi[k] = R.box_hi[k]; }
-            dim3 grid((Md.G.dim[2] - 2 * M + K::CZ - 1) / K::CZ, (Md.G.dim[1] - 2 * M + K::CY - 1) / K::CY, count);
+            const int nzint = (R.zstrip > 0 ? R.zstrip : Md.G.dim[2] - M) - M;   // z columns covered by tiles
+            dim3 grid((nzint + K::CZ - 1) / K::CZ, (Md.G.dim[1] - 2 * M + K::CY - 1) / K::CY, count);
             if (Md.p.hetero) fused_step<SO, ARITH, true><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
             else fused_step<SO, ARITH, false><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
             check();
+            if (R.zstrip > 0) {
+                // A few z columns are left over after the last full tile (1025 = 17 x 60 + 5 at 1024^3): a whole row of
+                // nearly empty CTAs would cost as much as a full one (5.5 % of the kernel).  Their stresses are computed
+                // per point here -- same arithmetic, same operands (level t0 only) -- and their velocities belong to
+                // the shell update, whose z-high slab starts at zstrip (velocity_shell).
+                const int xa = A.xs[chunk0], xb = A.xs[chunk0 + count];
+                dim3 blk(8, 32);
+                dim3 sg((Md.G.dim[2] - M - R.zstrip + blk.x - 1) / blk.x, (Md.G.dim[1] - 2 * M + blk.y - 1) / blk.y, xb - xa);
+                if (Md.p.hetero) stress_interior_h<SO, ARITH><<<sg, blk, 0, st>>>(ptrs(), media(), Md.G, Md.hc, t0, t1, xa, R.zstrip);
+                else stress_interior<SO, T, ARITH><<<sg, blk, 0, st>>>(ptrs(), Md.G, Md.sc, t0, t1, xa, R.zstrip);
+                check();
+            }
         }
     }
     // velocity update of the shell the fused kernel leaves out: interior minus [2m+1, dim-2m-1)^3,
@@ -741,6 +755,7 @@ struct Stepper {
             const int m = Md.m;
             int lo[3], hi[3], ilo[3], ihi[3];
             for (int d = 0; d < 3; ++d) { lo[d] = m; hi[d] = Md.G.dim[d] - m; ilo[d] = 2 * m + 1; ihi[d] = Md.G.dim[d] - 2 * m - 1; }
+            if (R.zstrip > 0 && R.zstrip < ihi[2]) ihi[2] = R.zstrip;   // the fused kernel stops at the z strip (fused())
             ShellBoxes B;
             int nb = 0, total = 0;
             for (int d = 0; d < 3; ++d)
@@ -889,7 +904,16 @@ int setup_fused(Run &R)
     // warm-up of every chunk negligible
     const int nsm = sm_count();
     const int CZ = m == 1 ? FusedCfg<1>::CZ : FusedCfg<2>::CZ, CY = OPESCI_FUSED_EY - 2 * m;
-    const long long tiles = (long long)((p.dim[2] - 2 * m + CZ - 1) / CZ) * ((p.dim[1] - 2 * m + CY - 1) / CY);
+    // z strip: when the last tile row would hold only a few columns, leave them to the per-point kernel
+    R.zstrip = 0;
+#ifndef OPESCI_ZSTRIP_MAX
+#define OPESCI_ZSTRIP_MAX 0   /* measured on B200 at 1024^3: the strip kernel costs more (+0.55 ms fused, +0.24 ms shell) than the row of nearly empty tiles it removes; kept for A/B */
+#endif
+    {
+        const int nzint = p.dim[2] - 2 * m, rem = nzint % CZ;
+        if (rem > 0 && rem <= OPESCI_ZSTRIP_MAX && nzint / CZ >= 2 && !(p.flags & OPESCI_OVERLAP)) R.zstrip = m + (nzint / CZ) * CZ;
+    }
+    const long long tiles = (long long)(((R.zstrip > 0 ? R.zstrip - m : p.dim[2] - 2 * m) + CZ - 1) / CZ) * ((p.dim[1] - 2 * m + CY - 1) / CY);
     const int nx = M.G.dim[0] - 2 * m;
     double best = -1.0;
     for (int nc = 1; nc <= 16; ++nc) {

@@ -33,6 +33,12 @@ CASES = [
     ("eigenwave3d_read", 2, [31, 30, 40], 6, False),
     ("eigenwave3d_read", 6, [33, 36, 34], 5, False),  # heterogeneous, tiled, Robertsson
     ("eigenwave3d_read", 4, [2, 3, 1], 3, False),     # heterogeneous on a minimal grid
+    # z strip of the fused path: interior z extent = 2 tiles of 60 + a few columns done per point (opesci_b200.cu:fused)
+    ("eigenwave3d", 4, [21, 26, 124], 6, False),      # 125 = 2 x 60 + 5 (the 1024^3 remainder)
+    ("eigenwave3d", 4, [20, 23, 120], 5, False),      # 121 = 2 x 60 + 1
+    ("eigenwave3d", 4, [19, 22, 127], 5, False),      # 128 = 2 x 60 + 8 (widest strip)
+    ("eigenwave3d", 2, [18, 21, 123], 5, False),      # so=2: tiles of 60, 124 = 2 x 60 + 4
+    ("eigenwave3d_read", 4, [17, 20, 125], 6, False), # heterogeneous strip
 ]
 
 

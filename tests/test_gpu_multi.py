@@ -35,7 +35,18 @@ def _free_port():
                                            (abi.ARITH_REFERENCE, "eigenwave3d_read", 4), (abi.ARITH_REFERENCE, "simplewave3d", 4),
                                            (abi.ARITH_REFERENCE, "eigenwave3d", 8), (abi.ARITH_REFERENCE, "eigenwave3d", 12)])
 def test_two_gpu_slabs_equal_single_gpu(arith, kind, so, cuda_lib, tmp_path):
-    cfg = dict(kind=kind, so=so, grid_size=[96, 70, 130], dt=0.002, steps=9, double=False,
+    _slabs_equal_single(arith, kind, so, [96, 70, 130], cuda_lib, tmp_path)
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
+@pytest.mark.parametrize("kind", ["eigenwave3d", "eigenwave3d_read"])
+def test_two_gpu_slabs_with_z_strip(kind, cuda_lib, tmp_path):
+    """interior z extent 125 = 2 tiles + 5 columns: the per-point z strip of the fused path, chunk by chunk"""
+    _slabs_equal_single(abi.ARITH_REFERENCE, kind, 4, [96, 40, 124], cuda_lib, tmp_path)
+
+
+def _slabs_equal_single(arith, kind, so, size, cuda_lib, tmp_path):
+    cfg = dict(kind=kind, so=so, grid_size=size, dt=0.002, steps=9, double=False,
                domain=[1.0, 0.9, 0.8], rho=1.2, vp=1.6, vs=0.8, seed=5)
     single = make_grid(cfg, flags=arith | abi.HOST_MIRROR_FULL)
     single.run(library=cuda_lib)
