@@ -135,9 +135,20 @@ template <int M> struct FusedCfg {
     // stored tile.  TMA needs the innermost box coordinate 16-B aligned (measured on B200: an
     // unaligned start raises "illegal instruction"), so tiles advance in multiples of 4 floats
     // along z and the box starts OFFZ >= M floats left of the stress tile.
-    static constexpr int CZ = (EZ - 2 * M) / 4 * 4, CY = EY - 2 * M;
-    static constexpr int OFFZ = (M + 3) / 4 * 4;
-    static constexpr int VZ = (EZ + M + OFFZ + 3) / 4 * 4, VY = EY + 2 * M;   // velocity tile delivered by TMA
+    // Sector-aligned stores (M = 2): the stored z range of a tile is [bx*CZ, bx*CZ + CZ) with CZ a multiple of 8 floats,
+    // so every row a CTA writes is made of whole 32-byte sectors.  With the tile origin at m + bx*60 (ZS = 0) each row
+    // started and ended inside a sector shared with the neighbouring CTA; written with streaming stores at different
+    // times, those partial sectors reach DRAM as read-modify-writes.  ZS = thread-tile shift: thread column tz is
+    // z = bx*CZ + tz - ZS; it has to stay even (8-byte global accesses of two z-adjacent points), hence M = 2 only.
+#ifndef OPESCI_FUSED_ALIGN
+#define OPESCI_FUSED_ALIGN 0   /* measured on B200: 20.2 vs 19.9 ms -- whole-sector stores, but 19 tile columns of 56 instead of 18 of 60 and 5 % more halo re-reads */
+#endif
+    static constexpr int ZS = (OPESCI_FUSED_ALIGN && M == 2) ? 2 : 0;
+    static constexpr int CZ = ZS ? (EZ - 2 * M) / 8 * 8 : (EZ - 2 * M) / 4 * 4, CY = EY - 2 * M;
+    static constexpr int OFFZ = (M + ZS + 3) / 4 * 4;
+    static constexpr int VZ = (EZ + M + OFFZ - ZS + 3) / 4 * 4, VY = EY + 2 * M;   // velocity tile delivered by TMA
+    // number of tiles along z for an array of dim3 = dim
+    static constexpr int ztiles(int dim) { return (dim - 2 * M + ZS + CZ - 1) / CZ; }
     static constexpr int RD = 2 * M + 2;                   // velocity ring depth (planes)
     static constexpr int SR = 4;                           // in-plane stress ring slots
     static constexpr int VTILE = ((VZ * VY * 4 + 127) / 128) * 128;   // bytes, 128-B aligned for TMA
@@ -235,7 +246,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
         if ((A.mode == 1) != inside) return;
     }
     const int tz = 2 * (tid % (K::EZ / 2)), ty = tid / (K::EZ / 2);          // lane 0 sits at tz, lane 1 at tz+1
-    const int ye = blockIdx.y * K::CY + ty, ze = blockIdx.x * K::CZ + tz;   // global coords of lane 0
+    const int ye = blockIdx.y * K::CY + ty, ze = blockIdx.x * K::CZ + tz - K::ZS;   // global coords of lane 0 (ze < 0: outside)
     const int chunk = blockIdx.z + A.chunk0;
     const int xa = A.xs[chunk];
     const int xb = A.xs[chunk + 1];
@@ -276,7 +287,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     for (int L = 0; L < 2; ++L) {
         const int z = ze + L, t = tz + L;
         const bool core = ty >= M && ty < M + K::CY && t >= M && t < M + K::CZ;
-        inb[L] = ye < G.dim[1] && z < G.dim[2];
+        inb[L] = ye < G.dim[1] && z >= 0 && z < G.dim[2];
         st_yz[L] = core && ye >= M && ye < G.dim[1] - M && z >= M && z < G.dim[2] - M;
         vf_yz[L] = core && ye >= 2 * M + 1 && ye < G.dim[1] - 2 * M - 1 && z >= 2 * M + 1 && z < G.dim[2] - 2 * M - 1;
     }
@@ -306,15 +317,34 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
         for (int k = 0; k < 2 * M + 1; ++k) txy[L][k] = txz[L][k] = 0;
     }
     T vself[2] = {0, 0}, wself[2] = {0, 0};   // V,W[t0] at plane xs-M (saved one iteration earlier)
-    const int lo = (ty + M) * K::VZ + tz + K::OFFZ;   // lane 0's element inside a velocity tile (even => 8-B aligned)
+    const int lo = (ty + M) * K::VZ + tz + K::OFFZ - K::ZS;   // lane 0's element inside a velocity tile (even => 8-B aligned)
     const T *vlo = vring + lo;
     T *slo = sring + ty * K::EZ + tz;
 
+#ifndef OPESCI_T0_BAND_POLICY
+#define OPESCI_T0_BAND_POLICY 0
+#endif
+#if OPESCI_T0_BAND_POLICY
+    // Rows / columns within 2M of a tile edge are read twice (once as this tile's data, once as the neighbour's
+    // recomputed halo): keep those in L2 (evict_last) and let the private middle of the tile go first (evict_first).
+    const bool band = ty < 2 * M || ty >= K::EY - 2 * M || tz < 2 * M || tz >= K::EZ - 2 * M;
+    uint64_t pol_last, pol_first;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+#if OPESCI_T0_BAND_POLICY == 2
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_first));
+#else
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+#endif
+    const uint64_t pol = band ? pol_last : pol_first;
+#endif
     auto load_told = [&](T (*told)[6], long long px) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             if (inb2) {
-#if OPESCI_T0_NOALLOC
+#if OPESCI_T0_BAND_POLICY
+                float2 v;
+                asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(gT0[k] + px), "l"(pol));
+#elif OPESCI_T0_NOALLOC
                 const float2 v = gload2_stream(gT0[k] + px);
 #else
                 const float2 v = *reinterpret_cast<const float2 *>(gT0[k] + px);

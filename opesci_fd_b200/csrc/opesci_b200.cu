@@ -727,8 +727,9 @@ struct Stepper {
             if (count <= 0) return;
             A.mode = mode;
             for (int k = 0; k < 3; ++k) { A.box_lo[k] = R.box_lo[k]; A.box_hi[k] = R.box_hi[k]; }
-            const int nzint = (R.zstrip > 0 ? R.zstrip : Md.G.dim[2] - M) - M;   // z columns covered by tiles
-            dim3 grid((nzint + K::CZ - 1) / K::CZ, (Md.G.dim[1] - 2 * M + K::CY - 1) / K::CY, count);
+            // z columns [M, zend) are covered by tiles; tile bx stores [bx*CZ + M - ZS, bx*CZ + M - ZS + CZ)
+            const int zend = R.zstrip > 0 ? R.zstrip : Md.G.dim[2] - M;
+            dim3 grid(K::ztiles(zend + M), (Md.G.dim[1] - 2 * M + K::CY - 1) / K::CY, count);
             if (Md.p.hetero) fused_step<SO, ARITH, true><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
             else fused_step<SO, ARITH, false><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
             check();
@@ -909,11 +910,13 @@ int setup_fused(Run &R)
 #ifndef OPESCI_ZSTRIP_MAX
 #define OPESCI_ZSTRIP_MAX 0   /* measured on B200 at 1024^3: the strip kernel costs more (+0.55 ms fused, +0.24 ms shell) than the row of nearly empty tiles it removes; kept for A/B */
 #endif
+    const int ZS = m == 1 ? FusedCfg<1>::ZS : FusedCfg<2>::ZS;
     {
-        const int nzint = p.dim[2] - 2 * m, rem = nzint % CZ;
-        if (rem > 0 && rem <= OPESCI_ZSTRIP_MAX && nzint / CZ >= 2 && !(p.flags & OPESCI_OVERLAP)) R.zstrip = m + (nzint / CZ) * CZ;
+        const int nzint = p.dim[2] - 2 * m + ZS, rem = nzint % CZ;   // tile bx stores z in [bx*CZ + m - ZS, +CZ)
+        if (rem > 0 && rem <= OPESCI_ZSTRIP_MAX && nzint / CZ >= 2 && !(p.flags & OPESCI_OVERLAP)) R.zstrip = m - ZS + (nzint / CZ) * CZ;
     }
-    const long long tiles = (long long)(((R.zstrip > 0 ? R.zstrip - m : p.dim[2] - 2 * m) + CZ - 1) / CZ) * ((p.dim[1] - 2 * m + CY - 1) / CY);
+    const int nztiles = ((R.zstrip > 0 ? R.zstrip : p.dim[2] - m) - m + ZS + CZ - 1) / CZ;
+    const long long tiles = (long long)nztiles * ((p.dim[1] - 2 * m + CY - 1) / CY);
     const int nx = M.G.dim[0] - 2 * m;
     double best = -1.0;
     for (int nc = 1; nc <= 16; ++nc) {
@@ -963,13 +966,13 @@ int setup_fused(Run &R)
         uniform(m, M.G.dim[0] - m, nc, 0);
         const int EY = OPESCI_FUSED_EY, EZ = OPESCI_FUSED_EZ;
         const int dims[3] = {M.G.dim[1], M.G.dim[2], M.G.dim[0]};
-        const int ntile[3] = {(p.dim[1] - 2 * m + CY - 1) / CY, (p.dim[2] - 2 * m + CZ - 1) / CZ, nc};
+        const int ntile[3] = {(p.dim[1] - 2 * m + CY - 1) / CY, nztiles, nc};
         for (int a = 0; a < 3; ++a) {
             int lo = ntile[a], hi = 0;
             for (int k = 0; k < ntile[a]; ++k) {
                 int rlo, rhi;   // read footprint [rlo, rhi)
                 if (a == 0) { rlo = k * CY - m; rhi = k * CY + EY + m; }
-                else if (a == 1) { rlo = k * CZ - m; rhi = k * CZ + EZ + m; }
+                else if (a == 1) { rlo = k * CZ - m - ZS; rhi = k * CZ + EZ + m - ZS; }
                 else {
                     const int xa = R.xs[k], xb = R.xs[k + 1];
                     rlo = xa - 2 * m; rhi = xb + 2 * m + 1;
