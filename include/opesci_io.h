@@ -28,19 +28,24 @@ extern "C" {
  * Here: when armed, opesci_execute copies the new time level of `field` to a page-locked staging
  * buffer on a second stream every `every` steps (the time loop only waits before it overwrites that
  * level again, two steps later) and a host callback on that stream writes
- * "<prefix><ti>.vts" with opesci_b200_dump_field_vts_3d.  fp64 fields are written as Float32
+ * "<prefix><ti>.vts" with opesci_b200_dump_field_vts_3d (the Points array, identical in every file of a series
+ * and three times the size of the field, is compressed once).  fp64 fields are written as Float32
  * (the reference's writer takes float*).  With x-slabs every rank writes the planes it owns to
  * "<prefix><ti>_r<rank>.vts".  every <= 0 or prefix == NULL disarms.  Applies to the next
  * opesci_execute calls of this process. */
 int opesci_b200_set_output(const char *prefix, int field, int every);
+/* zlib level (0-9) of every .vts written by this library.  Default 1: the reference asks VTK for level 9
+ * (src/opesciIO.cpp:653), which decompresses to the same bytes but costs ~10x the time -- it decides whether the
+ * output hides behind the time loop.  Returns -1 for a level outside 0-9. */
+int opesci_b200_set_output_level(int zlib_level);
 /* number of snapshot files written by the last opesci_execute and how many writes failed */
 int opesci_b200_output_stats(int *files_written, int *write_errors);
 
 /* Replaces: opesci_dump_field_vts_3d (src/opesciIO.cpp:614-667, include/opesciIO.h).
  * Writes `name`.vts: a VTK XML StructuredGrid, point (i,j,k) at ((i-margin)*spacing[0],
  * (j-margin)*spacing[1], (k-margin)*spacing[2]) in the reference's point order (k fastest), one
- * Float32 point-data array named "field", zlib level 9 like the reference's
- * vtkZLibDataCompressor (appended raw data, UInt32 block headers).  `x0` shifts the first index
+ * Float32 point-data array named "field", zlib-compressed like the reference's
+ * vtkZLibDataCompressor output (appended raw data, UInt32 block headers; level: opesci_b200_set_output_level).  `x0` shifts the first index
  * (a slab's first owned plane; 0 otherwise).  Returns 0, -1 on I/O failure. */
 int opesci_b200_dump_field_vts_3d(const char *name, const int dims[3], const float spacing[3], int margin,
                                   const float *field, int x0);

@@ -292,6 +292,12 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
         vf_yz[L] = core && ye >= 2 * M + 1 && ye < G.dim[1] - 2 * M - 1 && z >= 2 * M + 1 && z < G.dim[2] - 2 * M - 1;
     }
     const bool inb2 = inb[0] && inb[1], st2 = st_yz[0] && st_yz[1], vf2 = vf_yz[0] && vf_yz[1];
+#ifndef OPESCI_HALO_SKIP
+#define OPESCI_HALO_SKIP 0   /* measured on B200: 20.85 vs 20.05 ms -- fewer loads and flops, but 113 instead of 106 registers and a warp-level branch per plane */
+#endif
+    // The recomputed halo ROWS of the tile (a whole warp each) feed only the y-windows of the core rows next to them:
+    // Txy, Tyy, Tyz.  Their Txx, Tzz, Txz are never read by anyone, so those warps neither load nor update them.
+    const bool halo_row = OPESCI_HALO_SKIP && (ty < M || ty >= M + K::CY);
     const int xv_lo = max(xa, 2 * M + 1), xv_hi = min(xb, G.dim[0] - 2 * M - 1);
     const long long pyz = (long long)ye * G.s[1] + ze;
     const long long lv0 = (long long)A.t0 * G.level, lv1 = (long long)A.t1 * G.level;
@@ -340,6 +346,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     auto load_told = [&](T (*told)[6], long long px) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
+            if (halo_row && (k == 0 || k == 2 || k == 5)) { told[0][k] = told[1][k] = 0; continue; }
             if (inb2) {
 #if OPESCI_T0_BAND_POLICY
                 float2 v;
@@ -440,6 +447,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                     const float lam = med[L][0], mu = med[L][1];
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
+                        if (halo_row && a != 1) { tn[L][a] = 0; continue; }
                         T acc = told[L][a];
                         bool first = false;
                         if (a == 0) window_ref_arr_h<M, false, 2>(acc, first, ux[L], A.HC.c[0], A.HC.c2[0], lam, mu);
@@ -462,7 +470,8 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                         window_ref_arr_h<M, true, 1>(acc, first, wy_f[L], A.HC.c[1], A.HC.c2[1], med[L][3], 0.f);
                         tn[L][4] = acc;
                     }
-                    {
+                    if (halo_row) tn[L][5] = 0;
+                    else {
                         T acc = told[L][5]; bool first = false;   // Txz (mu13): D_z U, D_x W
                         window_ref_arr_h<M, true, 1>(acc, first, uz_f, A.HC.c[2], A.HC.c2[2], med[L][4], 0.f);
                         window_ref_arr_h<M, true, 1>(acc, first, wx[L], A.HC.c[0], A.HC.c2[0], med[L][4], 0.f);
@@ -472,15 +481,16 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                     const T du = window_fast_arr<M, T, false>(ux[L], A.HC.c[0]), dv = window_fast_arr<M, T, false>(vy_b[L], A.HC.c[1]),
                             dw = window_fast_arr<M, T, false>(wz_b, A.HC.c[2]);
                     const T tr = med[L][0] * (du + dv + dw), mu2 = 2.0f * med[L][1];
-                    tn[L][0] = told[L][0] + (tr + mu2 * du);
+                    tn[L][0] = halo_row ? 0.f : told[L][0] + (tr + mu2 * du);
                     tn[L][1] = told[L][1] + (tr + mu2 * dv);
-                    tn[L][2] = told[L][2] + (tr + mu2 * dw);
+                    tn[L][2] = halo_row ? 0.f : told[L][2] + (tr + mu2 * dw);
                     tn[L][3] = told[L][3] + med[L][2] * (window_fast_arr<M, T, true>(uy_f[L], A.HC.c[1]) + window_fast_arr<M, T, true>(vx[L], A.HC.c[0]));
                     tn[L][4] = told[L][4] + med[L][3] * (window_fast_arr<M, T, true>(vz_f, A.HC.c[2]) + window_fast_arr<M, T, true>(wy_f[L], A.HC.c[1]));
-                    tn[L][5] = told[L][5] + med[L][4] * (window_fast_arr<M, T, true>(uz_f, A.HC.c[2]) + window_fast_arr<M, T, true>(wx[L], A.HC.c[0]));
+                    tn[L][5] = halo_row ? 0.f : told[L][5] + med[L][4] * (window_fast_arr<M, T, true>(uz_f, A.HC.c[2]) + window_fast_arr<M, T, true>(wx[L], A.HC.c[0]));
                 } else if (ARITH == OPESCI_ARITH_REFERENCE) {
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
+                        if (halo_row && a != 1) { tn[L][a] = 0; continue; }
                         T acc = told[L][a];
                         bool first = false;
                         window_ref_arr<M, T, false>(acc, first, ux[L], A.C.sn[a][0]);
@@ -500,7 +510,8 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                         window_ref_arr<M, T, true>(acc, first, wy_f[L], A.C.ss[1][1]);
                         tn[L][4] = acc;
                     }
-                    {
+                    if (halo_row) tn[L][5] = 0;
+                    else {
                         T acc = told[L][5]; bool first = false;   // Txz: D_z U, D_x W
                         window_ref_arr<M, T, true>(acc, first, uz_f, A.C.ss[2][0]);
                         window_ref_arr<M, T, true>(acc, first, wx[L], A.C.ss[2][1]);
@@ -508,13 +519,15 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                     }
                 } else {
 #pragma unroll
-                    for (int a = 0; a < 3; ++a)
+                    for (int a = 0; a < 3; ++a) {
+                        if (halo_row && a != 1) { tn[L][a] = 0; continue; }
                         tn[L][a] = told[L][a] + (window_fast_arr<M, T, false>(ux[L], A.C.sn[a][0]) +
                                                  window_fast_arr<M, T, false>(vy_b[L], A.C.sn[a][1]) +
                                                  window_fast_arr<M, T, false>(wz_b, A.C.sn[a][2]));
+                    }
                     tn[L][3] = told[L][3] + (window_fast_arr<M, T, true>(uy_f[L], A.C.ss[0][0]) + window_fast_arr<M, T, true>(vx[L], A.C.ss[0][1]));
                     tn[L][4] = told[L][4] + (window_fast_arr<M, T, true>(vz_f, A.C.ss[1][0]) + window_fast_arr<M, T, true>(wy_f[L], A.C.ss[1][1]));
-                    tn[L][5] = told[L][5] + (window_fast_arr<M, T, true>(uz_f, A.C.ss[2][0]) + window_fast_arr<M, T, true>(wx[L], A.C.ss[2][1]));
+                    tn[L][5] = halo_row ? (T)0 : told[L][5] + (window_fast_arr<M, T, true>(uz_f, A.C.ss[2][0]) + window_fast_arr<M, T, true>(wx[L], A.C.ss[2][1]));
                 }
             }
             // ---- store the new stresses (owned tile, owned planes), prefetch next T[t0]

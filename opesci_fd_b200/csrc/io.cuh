@@ -29,7 +29,20 @@ namespace opesci_io {
 // One appended-data array: zlib blocks with the UInt32 header [nblocks, blocksize, lastblocksize, csize...]
 // (the layout vtkXMLWriter emits for compressor="vtkZLibDataCompressor", header_type UInt32).
 // `fill(dst, first_byte, nbytes)` produces the raw bytes of [first_byte, first_byte + nbytes).
-template <typename Fill> bool append_compressed(FILE *fp, size_t total_bytes, Fill fill, size_t *written)
+// zlib level of the .vts writers.  The reference asks VTK for level 9 (src/opesciIO.cpp:653); the decompressed
+// bytes are the same at any level, and level 9 costs ~10x the time of level 1 on field data, which is what decides
+// whether the per-step output can hide behind the time loop.  opesci_b200_set_output_level() changes it.
+inline int &zlib_level() { static int level = 1; return level; }
+
+// an appended array already in its on-disk form (header + compressed blocks): the Points array of a snapshot series
+// is the same in every file and three times the size of the field, so it is compressed once
+struct PackedArray {
+    std::vector<unsigned char> bytes;
+    int dims[3] = {0, 0, 0}, margin = 0, x0 = 0, level = -1;
+    float spacing[3] = {0, 0, 0};
+};
+
+template <typename Fill> bool append_compressed(FILE *fp, size_t total_bytes, Fill fill, size_t *written, PackedArray *keep = nullptr)
 {
     const size_t BS = (size_t)1 << 20;
     const size_t nblocks = total_bytes ? (total_bytes + BS - 1) / BS : 0;
@@ -37,6 +50,7 @@ template <typename Fill> bool append_compressed(FILE *fp, size_t total_bytes, Fi
     std::vector<std::vector<unsigned char>> out(nblocks);
     std::atomic<size_t> next(0);
     std::atomic<bool> ok(true);
+    const int level = zlib_level();
     auto work = [&]() {
         std::vector<unsigned char> raw(BS);
         for (;;) {
@@ -46,7 +60,7 @@ template <typename Fill> bool append_compressed(FILE *fp, size_t total_bytes, Fi
             fill(raw.data(), b * BS, n);
             uLongf cap = compressBound((uLong)n);
             out[b].resize(cap);
-            if (compress2(out[b].data(), &cap, raw.data(), (uLong)n, 9) != Z_OK) { ok = false; break; }   // level 9: src/opesciIO.cpp:653
+            if (compress2(out[b].data(), &cap, raw.data(), (uLong)n, level) != Z_OK) { ok = false; break; }
             out[b].resize(cap);
         }
     };
@@ -65,8 +79,10 @@ template <typename Fill> bool append_compressed(FILE *fp, size_t total_bytes, Fi
     for (size_t b = 0; b < nblocks; ++b) head[3 + b] = (uint32_t)out[b].size();
     size_t w = head.size() * 4;
     if (fwrite(head.data(), 4, head.size(), fp) != head.size()) return false;
+    if (keep) keep->bytes.assign((const unsigned char *)head.data(), (const unsigned char *)head.data() + w);
     for (size_t b = 0; b < nblocks; ++b) {
         if (fwrite(out[b].data(), 1, out[b].size(), fp) != out[b].size()) return false;
+        if (keep) keep->bytes.insert(keep->bytes.end(), out[b].begin(), out[b].end());
         w += out[b].size();
     }
     *written = w;
@@ -75,7 +91,7 @@ template <typename Fill> bool append_compressed(FILE *fp, size_t total_bytes, Fi
 
 // field values as Float32 from a float or double source
 template <typename T>
-int dump_vts(const char *name, const int dims[3], const float spacing[3], int margin, const T *field, int x0)
+int dump_vts(const char *name, const int dims[3], const float spacing[3], int margin, const T *field, int x0, PackedArray *points_cache = nullptr)
 {
     const std::string path = std::string(name) + ".vts";
     const size_t npts = (size_t)dims[0] * dims[1] * dims[2];
@@ -94,16 +110,31 @@ int dump_vts(const char *name, const int dims[3], const float spacing[3], int ma
     }, &w_field);
     // points in the reference's order: i (dims[0]) slowest, k (dims[2]) fastest; coordinate = (index - margin) * spacing
     // evaluated in float like the reference (src/opesciIO.cpp:623-629)
-    ok = ok && append_compressed(fb, npts * 12, [&](unsigned char *dst, size_t first, size_t n) {
-        float *d = (float *)dst;
-        const size_t c0 = first / 4, nc = n / 4;   // float components; 1 MiB blocks are a multiple of 4 B, not of 12 B
-        for (size_t c = 0; c < nc; ++c) {
-            const size_t comp = c0 + c, pt = comp / 3;
-            const int which = (int)(comp % 3);
-            const int k = (int)(pt % dims[2]), j = (int)((pt / dims[2]) % dims[1]), i = (int)(pt / ((size_t)dims[2] * dims[1]));
-            d[c] = which == 0 ? (float)(i + x0 - margin) * spacing[0] : which == 1 ? (float)(j - margin) * spacing[1] : (float)(k - margin) * spacing[2];
+    const bool cached = points_cache && !points_cache->bytes.empty() && points_cache->level == zlib_level() && points_cache->margin == margin &&
+                        points_cache->x0 == x0 && memcmp(points_cache->dims, dims, sizeof points_cache->dims) == 0 &&
+                        memcmp(points_cache->spacing, spacing, sizeof points_cache->spacing) == 0;
+    if (cached) {
+        ok = ok && fwrite(points_cache->bytes.data(), 1, points_cache->bytes.size(), fb) == points_cache->bytes.size();
+        w_pts = points_cache->bytes.size();
+    } else {
+        if (points_cache) {
+            memcpy(points_cache->dims, dims, sizeof points_cache->dims);
+            memcpy(points_cache->spacing, spacing, sizeof points_cache->spacing);
+            points_cache->margin = margin; points_cache->x0 = x0; points_cache->level = zlib_level();
+            points_cache->bytes.clear();
         }
-    }, &w_pts);
+        ok = ok && append_compressed(fb, npts * 12, [&](unsigned char *dst, size_t first, size_t n) {
+            float *d = (float *)dst;
+            const size_t c0 = first / 4, nc = n / 4;   // float components; 1 MiB blocks are a multiple of 4 B, not of 12 B
+            for (size_t c = 0; c < nc; ++c) {
+                const size_t comp = c0 + c, pt = comp / 3;
+                const int which = (int)(comp % 3);
+                const int k = (int)(pt % dims[2]), j = (int)((pt / dims[2]) % dims[1]), i = (int)(pt / ((size_t)dims[2] * dims[1]));
+                d[c] = which == 0 ? (float)(i + x0 - margin) * spacing[0] : which == 1 ? (float)(j - margin) * spacing[1] : (float)(k - margin) * spacing[2];
+            }
+        }, &w_pts, points_cache);
+        if (!ok && points_cache) points_cache->bytes.clear();
+    }
     ok = (fclose(fb) == 0) && ok;
     if (!ok) { remove(tmp.c_str()); return -1; }
     FILE *fp = fopen(path.c_str(), "wb");
@@ -169,6 +200,7 @@ struct Snapshotter {
     std::condition_variable cv;
     std::thread writer;
     struct Job { int stage, ti; };
+    PackedArray points;                   // the Points array of this series, compressed once
     std::vector<Job> queue;
     bool quit = false;
 
@@ -197,8 +229,8 @@ struct Snapshotter {
             char name[1024];
             if (nranks > 1) snprintf(name, sizeof name, "%s%d_r%d", cfg.prefix.c_str(), j.ti, rank);
             else snprintf(name, sizeof name, "%s%d", cfg.prefix.c_str(), j.ti);
-            const int rc = esz == 4 ? dump_vts<float>(name, dims, spacing, margin, (const float *)stage[j.stage], x0)
-                                    : dump_vts<double>(name, dims, spacing, margin, (const double *)stage[j.stage], x0);
+            const int rc = esz == 4 ? dump_vts<float>(name, dims, spacing, margin, (const float *)stage[j.stage], x0, &points)
+                                    : dump_vts<double>(name, dims, spacing, margin, (const double *)stage[j.stage], x0, &points);
             if (rc == 0) files_written()++;
             else write_errors()++;
             {
@@ -387,6 +419,13 @@ int opesci_b200_set_output(const char *prefix, int field, int every)
     c.prefix = prefix ? prefix : "";
     c.field = field;
     c.every = every > 0 ? every : 1;
+    return 0;
+}
+
+int opesci_b200_set_output_level(int zlib_level)
+{
+    if (zlib_level < 0 || zlib_level > 9) return -1;
+    opesci_io::zlib_level() = zlib_level;
     return 0;
 }
 

@@ -201,6 +201,15 @@ def test_vts_writer_round_trip(lib, tmp_path):
     ext, f, pts = read_vts(name + ".vts")
     assert np.array_equal(f, big) and pts[0, 0] == np.float32(8) * sp[0] and pts[-1, 2] == np.float32(298) * sp[2]
     assert lib.opesci_b200_dump_field_vts_3d(b"/nonexistent_dir/x", dims, fptr(sp), 2, fptr(big), 0) == -1
+    # the reference's level 9 gives the same data in a smaller file
+    size1 = os.path.getsize(name + ".vts")
+    assert lib.opesci_b200_set_output_level(10) == -1 and lib.opesci_b200_set_output_level(9) == 0
+    try:
+        assert lib.opesci_b200_dump_field_vts_3d(name.encode(), dims, fptr(sp), 2, fptr(big), 10) == 0
+    finally:
+        lib.opesci_b200_set_output_level(1)
+    _, f9, p9 = read_vts(name + ".vts")
+    assert np.array_equal(f9, big) and np.array_equal(p9, pts) and os.path.getsize(name + ".vts") <= size1
 
 
 # ------------------------------------------------------------------ GPU
