@@ -50,6 +50,11 @@ int opesci_b200_output_stats(int *files_written, int *write_errors);
 int opesci_b200_dump_field_vts_3d(const char *name, const int dims[3], const float spacing[3], int margin,
                                   const float *field, int x0);
 
+/* Replaces: opesci_dump_field_vts (src/opesciIO.cpp:143-194), the writer of src/segy2vts.cpp: field[i + j*dims[0] +
+ * k*dims[0]*dims[1]] (x fastest, the layout-0 vectors of the SEG-Y reader), point (i,j,k) at (i*spacing[0],
+ * j*spacing[1], k*spacing[2]).  `python -m opesci_fd_b200.segy2vts model.segy` is the converter built on it. */
+int opesci_b200_dump_field_vts(const char *name, const int dims[3], const float spacing[3], const float *field);
+
 /* ---- model input ------------------------------------------------------------ */
 /* Replaces: opesci_read_simple_binary_ptr (src/opesciIO.cpp:319-342): flat float32 file into
  * array[0..size).  Returns 0; -1 if the file cannot be opened; -2 if it holds fewer than `size`

@@ -107,6 +107,7 @@ EXPORTED_SYMBOLS = [
 # include/opesci_io.h (model input / field output around the path)
 IO_SYMBOLS = [
     "opesci_b200_set_output", "opesci_b200_set_output_level", "opesci_b200_output_stats", "opesci_b200_dump_field_vts_3d",
+    "opesci_b200_dump_field_vts",
     "opesci_b200_read_simple_binary_ptr", "opesci_b200_simple_binary_count", "opesci_b200_read_model_segy",
     "opesci_b200_segy_decode_device", "opesci_b200_ibm_to_float", "opesci_b200_read_xyz",
     "opesci_b200_resample_timeseries", "opesci_b200_calculate_dt", "opesci_b200_calculate_lame_constants",
@@ -172,6 +173,8 @@ def bind_io(lib):
     lib.opesci_b200_output_stats.restype = c_int
     lib.opesci_b200_dump_field_vts_3d.argtypes = [c_char_p, PI, PF, c_int, PF, c_int]
     lib.opesci_b200_dump_field_vts_3d.restype = c_int
+    lib.opesci_b200_dump_field_vts.argtypes = [c_char_p, PI, PF, PF]
+    lib.opesci_b200_dump_field_vts.restype = c_int
     lib.opesci_b200_read_simple_binary_ptr.argtypes = [c_char_p, PF, c_size_t]
     lib.opesci_b200_read_simple_binary_ptr.restype = c_int
     lib.opesci_b200_simple_binary_count.argtypes = [c_char_p]

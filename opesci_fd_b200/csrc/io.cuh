@@ -90,8 +90,11 @@ template <typename Fill> bool append_compressed(FILE *fp, size_t total_bytes, Fi
 }
 
 // field values as Float32 from a float or double source
+// xfast = false: field[(i*dims[1] + j)*dims[2] + k], the generated code's [x][y][z] arrays (opesci_dump_field_vts_3d);
+// xfast = true:  field[i + j*dims[0] + k*dims[0]*dims[1]], the model vectors of the SEG-Y reader (opesci_dump_field_vts)
 template <typename T>
-int dump_vts(const char *name, const int dims[3], const float spacing[3], int margin, const T *field, int x0, PackedArray *points_cache = nullptr)
+int dump_vts(const char *name, const int dims[3], const float spacing[3], int margin, const T *field, int x0, PackedArray *points_cache = nullptr,
+             bool xfast = false)
 {
     const std::string path = std::string(name) + ".vts";
     const size_t npts = (size_t)dims[0] * dims[1] * dims[2];
@@ -129,7 +132,9 @@ int dump_vts(const char *name, const int dims[3], const float spacing[3], int ma
             for (size_t c = 0; c < nc; ++c) {
                 const size_t comp = c0 + c, pt = comp / 3;
                 const int which = (int)(comp % 3);
-                const int k = (int)(pt % dims[2]), j = (int)((pt / dims[2]) % dims[1]), i = (int)(pt / ((size_t)dims[2] * dims[1]));
+                int i, j, k;
+                if (xfast) { i = (int)(pt % dims[0]); j = (int)((pt / dims[0]) % dims[1]); k = (int)(pt / ((size_t)dims[0] * dims[1])); }
+                else { k = (int)(pt % dims[2]); j = (int)((pt / dims[2]) % dims[1]); i = (int)(pt / ((size_t)dims[2] * dims[1])); }
                 d[c] = which == 0 ? (float)(i + x0 - margin) * spacing[0] : which == 1 ? (float)(j - margin) * spacing[1] : (float)(k - margin) * spacing[2];
             }
         }, &w_pts, points_cache);
@@ -154,7 +159,7 @@ int dump_vts(const char *name, const int dims[3], const float spacing[3], int ma
             "    </Piece>\n"
             "  </StructuredGrid>\n"
             "  <AppendedData encoding=\"raw\">\n   _",
-            dims[2] - 1, dims[1] - 1, dims[0] - 1, dims[2] - 1, dims[1] - 1, dims[0] - 1, w_field);
+            dims[xfast ? 0 : 2] - 1, dims[1] - 1, dims[xfast ? 2 : 0] - 1, dims[xfast ? 0 : 2] - 1, dims[1] - 1, dims[xfast ? 2 : 0] - 1, w_field);
     FILE *fr = fopen(tmp.c_str(), "rb");
     bool good = fr != nullptr;
     if (fr) {
@@ -440,6 +445,12 @@ int opesci_b200_dump_field_vts_3d(const char *name, const int dims[3], const flo
 {
     if (!name || !dims || !spacing || !field) return -1;
     return opesci_io::dump_vts<float>(name, dims, spacing, margin, field, x0);
+}
+
+int opesci_b200_dump_field_vts(const char *name, const int dims[3], const float spacing[3], const float *field)
+{
+    if (!name || !dims || !spacing || !field) return -1;
+    return opesci_io::dump_vts<float>(name, dims, spacing, 0, field, 0, nullptr, true);
 }
 
 int64_t opesci_b200_simple_binary_count(const char *filename)

@@ -357,3 +357,22 @@ def test_gpu_heterogeneous_media_from_segy(lib, tmp_path):
         g.free()
     assert np.isfinite(out[0]).all() and np.abs(out[0]).max() > 0
     assert np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32))
+
+
+def test_segy2vts_converter(lib, gold, tmp_path):
+    """src/segy2vts.cpp: SEG-Y volume -> <base>.vts through the reader and the x-fastest writer"""
+    import shutil
+    from opesci_fd_b200 import segy2vts
+    src = str(tmp_path / "model.segy")
+    shutil.copy(os.path.join(GOLD, "io_model_be.segy"), src)
+    out, dim, spacing = segy2vts.convert(src, library=lib)
+    assert out == str(tmp_path / "model.vts") and dim == list(gold["segy_be_dim"])
+    ext, f, pts = read_vts(out)
+    assert ext == [0, dim[0] - 1, 0, dim[1] - 1, 0, dim[2] - 1]          # x fastest: VTK's own convention
+    assert np.array_equal(f.view(np.uint32), gold["segy_be_array_bits"])
+    k, j, i = np.meshgrid(np.arange(dim[2]), np.arange(dim[1]), np.arange(dim[0]), indexing="ij")
+    sp = np.array(spacing, dtype=np.float32)
+    want = np.stack([i.astype(np.float32) * sp[0], j.astype(np.float32) * sp[1], k.astype(np.float32) * sp[2]], -1).reshape(-1, 3)
+    assert np.array_equal(pts, want)
+    with pytest.raises(ValueError):
+        segy2vts.convert(str(tmp_path / "model.dat"), library=lib)
