@@ -40,6 +40,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
@@ -238,6 +242,9 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     T *sring = reinterpret_cast<T *>(smem + (size_t)3 * RD * K::VTILE);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)3 * RD * K::VTILE + (size_t)5 * K::SR * K::STILE);
 
+#ifndef OPESCI_SPLIT_BARRIER
+#define OPESCI_SPLIT_BARRIER 0
+#endif
     const GridGeom &G = A.G;
     const int tid = threadIdx.x;
     if (A.mode != 0) {
@@ -261,6 +268,9 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 
     if (tid == 0) {
         for (int i = 0; i < 3 * RD; ++i) mbar_init(&bars[i], 1);
+#if OPESCI_SPLIT_BARRIER
+        mbar_init(&bars[3 * RD], K::THREADS / 32);   // step barrier: one arrival per warp and plane
+#endif
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -363,9 +373,18 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             }
         }
     };
-    T told[2][6];
+#ifndef OPESCI_T0_AHEAD
+#define OPESCI_T0_AHEAD 1
+#endif
+    // T[t0] of the planes ahead: AHEAD = 1 keeps one plane in registers, AHEAD = 2 two (buffers alternate with the
+    // parity of the unrolled plane index r; RD is even)
+    T told_buf[OPESCI_T0_AHEAD][2][6];
     long long px = (long long)xs_begin * sx;
-    load_told(told, px);
+    load_told(told_buf[0], px);
+#if OPESCI_T0_AHEAD == 2
+    static_assert(RD % 2 == 0, "plane parity must survive the unrolled loop");
+    if (xs_begin + 1 < xs_end) load_told(told_buf[1], px + sx);
+#endif
 
     // planes of the first window (first use of their slots: phase parity 0)
 #pragma unroll
@@ -380,6 +399,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
         for (int r = 0; r < RD; ++r) {
             const int xs = xs0 + r;
             if (xs >= xs_end) break;
+            T (*told)[6] = told_buf[r % OPESCI_T0_AHEAD];
             // heterogeneous mode: lambda, mu, mu12, mu23, mu13 of the two cells (plane xs), issued before the waits so
             // that their latency overlaps the TMA wait and the operand gather
             T med[2][5];
@@ -544,7 +564,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                 }
             }
             px += sx;
-            if (xs + 1 < xs_end) load_told(told, px);
+            if (xs + OPESCI_T0_AHEAD < xs_end) load_told(told, px + (OPESCI_T0_AHEAD - 1) * sx);
             // ---- shift the register windows, publish the in-plane operands
 #pragma unroll
             for (int L = 0; L < 2; ++L) {
@@ -556,6 +576,16 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                 txy[L][2 * M] = tn[L][3];
                 txz[L][2 * M] = tn[L][5];
             }
+#if OPESCI_SPLIT_BARRIER
+            // Split-phase step barrier instead of a rendezvous: a warp ARRIVES once it has gathered its operands of plane
+            // xs and published its stresses, and only WAITS -- here, one plane later -- for everybody's arrival of the
+            // previous plane.  That covers all three hazards with a plane of slack: the slot written below was last read
+            // by the velocity phase two planes ago (before that warp's previous arrival); the slots the velocity phase
+            // reads were published two planes ago; and the TMA refill of the previous plane's dead slot (thread 0,
+            // below) follows every warp's gather of that plane.  Warps may drift up to one plane apart, so the
+            // shared-memory phase of one overlaps the arithmetic of another.
+            if (xs > xs_begin) mbar_wait(&bars[3 * RD], (uint32_t)((r + 1) & 1));
+#endif
             {
                 T *s = slo + (xs & (K::SR - 1)) * ST;
                 *reinterpret_cast<float2 *>(s + 0 * K::SR * ST) = make_float2(tn[0][3], tn[1][3]);   // Txy
@@ -575,19 +605,29 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                     bet[0][k] = v.x; bet[1][k] = v.y;
                 }
             }
+#if OPESCI_SPLIT_BARRIER
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&bars[3 * RD]);
+            // ---- the oldest planes of the PREVIOUS iteration (slot r-1) are dead for every warp: refill their slots
+            if (tid == 0 && xs > xs_begin) {
+                const int rp = (r + RD - 1) % RD;
+                const int pU = xs - 1 - M + RD, pVW = xs - M + RD;
+#else
             __syncthreads();
             // ---- the oldest planes (window entry 0, slot r) are dead: refill their slots
             if (tid == 0) {
+                const int rp = r;
                 const int pU = xs - M + RD, pVW = xs - M + 1 + RD;
+#endif
                 if (pU <= lastU) {
-                    mbar_arrive_expect_tx(&bars[0 * RD + r], TILE_BYTES);
-                    tma_load_3d((void *)(vring + (0 * RD + r) * VT), &tmU, &bars[0 * RD + r], c0, c1, lvl0 + pU);
+                    mbar_arrive_expect_tx(&bars[0 * RD + rp], TILE_BYTES);
+                    tma_load_3d((void *)(vring + (0 * RD + rp) * VT), &tmU, &bars[0 * RD + rp], c0, c1, lvl0 + pU);
                 }
                 if (pVW <= lastVW) {
-                    mbar_arrive_expect_tx(&bars[1 * RD + r], TILE_BYTES);
-                    tma_load_3d((void *)(vring + (1 * RD + r) * VT), &tmV, &bars[1 * RD + r], c0, c1, lvl0 + pVW);
-                    mbar_arrive_expect_tx(&bars[2 * RD + r], TILE_BYTES);
-                    tma_load_3d((void *)(vring + (2 * RD + r) * VT), &tmW, &bars[2 * RD + r], c0, c1, lvl0 + pVW);
+                    mbar_arrive_expect_tx(&bars[1 * RD + rp], TILE_BYTES);
+                    tma_load_3d((void *)(vring + (1 * RD + rp) * VT), &tmV, &bars[1 * RD + rp], c0, c1, lvl0 + pVW);
+                    mbar_arrive_expect_tx(&bars[2 * RD + rp], TILE_BYTES);
+                    tma_load_3d((void *)(vring + (2 * RD + rp) * VT), &tmW, &bars[2 * RD + rp], c0, c1, lvl0 + pVW);
                 }
             }
             // ---- velocities of plane xv = xs - M from the new stresses xv-M .. xv+M
