@@ -238,11 +238,11 @@ def main():
         dom_name, dom_ms, dom_bytes = "stress_interior (two-pass path: 15 words/pt)", kms[0], 60.0 * pts_gpu
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture
-    # (profiles/r01_fused_v3_ncu_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum); only known for
+    # (profiles/r01b_fused_ncu_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum); only known for
     # the configuration that capture was taken on
     traffic = None
     if fused and world == 1 and n == 1024:
-        traffic = 50.459014e9 + 39.164710e9
+        traffic = 50.320062e9 + 39.194970e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "algorithmic_bytes_per_launch": dom_bytes,
                 "kernel": dom_name, "kernel_ms": dom_ms, "peak_source": peak_src,
