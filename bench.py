@@ -316,7 +316,10 @@ def main():
 
 if __name__ == "__main__":
     # stdout carries exactly ONE line (the JSON record); everything else the run prints goes to stderr
-    _real_stdout = sys.stdout
+    # (redirected at the file-descriptor level: NCCL prints its version banner with printf)
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     sys.stdout = sys.stderr
     _orig_print = print
 

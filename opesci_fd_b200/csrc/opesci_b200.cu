@@ -597,7 +597,9 @@ struct Stepper {
     bool sides_independent() const
     {
         const Model &M = R.M;
-        if (M.slab.nranks > 1) return false;   // slabs: keep the reference's loop order literally
+        // slabs: keep the reference's loop order literally.  (Measured: pairing the sides on slab ranks breaks the
+        // bit-exact agreement with the single-domain run and gains nothing, 90.4 vs 90.6 Gpts/s on 2 GPUs.)
+        if (M.slab.nranks > 1) return false;
         for (int d = 0; d < 3; ++d)
             if (M.G.dim[d] < 4 * M.m + 6) return false;
         return true;
