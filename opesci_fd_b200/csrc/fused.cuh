@@ -153,8 +153,14 @@ template <int M> struct FusedCfg {
     static constexpr int VZ = (EZ + M + OFFZ - ZS + 3) / 4 * 4, VY = EY + 2 * M;   // velocity tile delivered by TMA
     // number of tiles along z for an array of dim3 = dim
     static constexpr int ztiles(int dim) { return (dim - 2 * M + ZS + CZ - 1) / CZ; }
-    static constexpr int RD = 2 * M + 2;                   // velocity ring depth (planes)
-    static constexpr int SR = 4;                           // in-plane stress ring slots
+#ifndef OPESCI_FUSED_RD_EXTRA
+#define OPESCI_FUSED_RD_EXTRA 0     /* A/B: extra planes of TMA prefetch */
+#endif
+#ifndef OPESCI_FUSED_SR
+#define OPESCI_FUSED_SR 4           /* (1 only makes sense with OPESCI_SKELETON) */
+#endif
+    static constexpr int RD = 2 * M + 2 + OPESCI_FUSED_RD_EXTRA;   // velocity ring depth (planes)
+    static constexpr int SR = OPESCI_FUSED_SR;             // in-plane stress ring slots
     static constexpr int VTILE = ((VZ * VY * 4 + 127) / 128) * 128;   // bytes, 128-B aligned for TMA
     static constexpr int STILE = EZ * EY * 4;
     static constexpr int SMEM = 3 * RD * VTILE + 5 * SR * STILE + 3 * RD * 8 + 128;
@@ -174,6 +180,8 @@ struct FusedArgs {
     // Tile subset of this launch.  The tiles inside the box [box_lo, box_hi) (tile_y, tile_z, chunk)
     // neither read nor write any cell the ghost-cell loops / shell update of the PREVIOUS step touch,
     // so they can run concurrently with those loops; the remaining tiles run afterwards.
+    int *pace;        // OPESCI_PACE: progress of every tile (plane index; -1 not started; INT_MAX done), else null
+    int cluster_sync; // launched as clusters of OPESCI_CLUSTER_Z z-adjacent CTAs (A/B experiment)
     int mode;         // 0: every tile, 1: only tiles inside the box, 2: only tiles outside the box
     int box_lo[3], box_hi[3];
 };
@@ -203,8 +211,18 @@ __device__ __forceinline__ float2 gload2_stream(const float *p)
     asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
     return v;
 }
+#ifndef OPESCI_SKEL_NOSTORE
+#define OPESCI_SKEL_NOSTORE 0   /* diagnostics of the memory skeleton: drop one class of traffic */
+#endif
+#ifndef OPESCI_SKEL_NOT0
+#define OPESCI_SKEL_NOT0 0
+#endif
 __device__ __forceinline__ void gstore(float *p, float v)
 {
+#if OPESCI_SKEL_NOSTORE
+    if (v == 123.456f) *p = v;
+    return;
+#endif
 #if OPESCI_STREAM_STORES
     __stcs(p, v);
 #else
@@ -213,6 +231,10 @@ __device__ __forceinline__ void gstore(float *p, float v)
 }
 __device__ __forceinline__ void gstore2(float *p, float a, float b)
 {
+#if OPESCI_SKEL_NOSTORE
+    if (a == 123.456f) *p = b;
+    return;
+#endif
 #if OPESCI_STREAM_STORES
     __stcs(reinterpret_cast<float2 *>(p), make_float2(a, b));
 #else
@@ -244,6 +266,15 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 
 #ifndef OPESCI_SPLIT_BARRIER
 #define OPESCI_SPLIT_BARRIER 0
+#endif
+#ifndef OPESCI_SKELETON
+#define OPESCI_SKELETON 0
+#endif
+#ifndef OPESCI_PACE
+#define OPESCI_PACE 0   /* > 0: a tile never runs more than this many planes ahead of a running y-neighbour (A/B experiment) */
+#endif
+#ifndef OPESCI_CLUSTER_Z
+#define OPESCI_CLUSTER_Z 1   /* > 1: z-adjacent CTAs form a thread-block cluster and march in lockstep (cluster barrier per plane) */
 #endif
     const GridGeom &G = A.G;
     const int tid = threadIdx.x;
@@ -357,6 +388,9 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             if (halo_row && (k == 0 || k == 2 || k == 5)) { told[0][k] = told[1][k] = 0; continue; }
+#if OPESCI_SKEL_NOT0
+            told[0][k] = told[1][k] = (T)k; continue;
+#endif
             if (inb2) {
 #if OPESCI_T0_BAND_POLICY
                 float2 v;
@@ -400,6 +434,24 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             const int xs = xs0 + r;
             if (xs >= xs_end) break;
             T (*told)[6] = told_buf[r % OPESCI_T0_AHEAD];
+#if OPESCI_PACE > 0
+            if (r == 0 && A.pace) {
+                if (tid == 0) {
+                    volatile int *pg = A.pace + ((size_t)chunk * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+                    *pg = xs;
+                    // neighbours that have not started (-1) or have finished (INT_MAX) never hold anybody back, and the
+                    // tile that is furthest behind waits for nobody: no deadlock
+                    for (int dy = -1; dy <= 1; dy += 2) {
+                        const int by = (int)blockIdx.y + dy;
+                        if (by < 0 || by >= (int)gridDim.y) continue;
+                        volatile int *pn = pg + dy * (int)gridDim.x;
+                        int v = *pn;
+                        while (v >= 0 && v < xs - OPESCI_PACE) { __nanosleep(200); v = *pn; }
+                    }
+                }
+                __syncthreads();
+            }
+#endif
             // heterogeneous mode: lambda, mu, mu12, mu23, mu13 of the two cells (plane xs), issued before the waits so
             // that their latency overlaps the TMA wait and the operand gather
             T med[2][5];
@@ -550,6 +602,14 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                     tn[L][5] = halo_row ? (T)0 : told[L][5] + (window_fast_arr<M, T, true>(uz_f, A.C.ss[2][0]) + window_fast_arr<M, T, true>(wx[L], A.C.ss[2][1]));
                 }
             }
+#if OPESCI_SKELETON
+            // DIAGNOSTIC ONLY (wrong results): keep every global load / store, TMA transfer, barrier and the shared-memory
+            // publish, drop the operand gathers and the arithmetic -- how long does the memory skeleton of the kernel take?
+#pragma unroll
+            for (int L = 0; L < 2; ++L)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) tn[L][k] = told[L][k] + ux[L][0];
+#endif
             // ---- store the new stresses (owned tile, owned planes), prefetch next T[t0]
             if (xs >= xa && xs < xb) {
                 if (st2) {
@@ -630,6 +690,13 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                     tma_load_3d((void *)(vring + (2 * RD + rp) * VT), &tmW, &bars[2 * RD + rp], c0, c1, lvl0 + pVW);
                 }
             }
+#if OPESCI_CLUSTER_Z > 1
+            // lockstep with the z-neighbours of the cluster: their row pieces of the same plane reach L2 / DRAM together
+            if (A.cluster_sync) {
+                asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+                asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            }
+#endif
             // ---- velocities of plane xv = xs - M from the new stresses xv-M .. xv+M
             const int xv = xs - M;
             if ((vf_yz[0] || vf_yz[1]) && xv >= xv_lo && xv < xv_hi) {
@@ -710,6 +777,10 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                                                  window_fast_arr<M, T, true>(zz_zf, A.C.v[2][2]));
                     }
                 }
+#if OPESCI_SKELETON
+#pragma unroll
+                for (int L = 0; L < 2; ++L) { vout[L][0] = uself[L] + xy_yb[L][0]; vout[L][1] = vself[L] + fxz[2 + L]; vout[L][2] = wself[L] + txx[L][0]; }
+#endif
                 const long long pxv = px - (long long)(M + 1) * sx;   // px already points at plane xs+1
                 if (vf2) {
 #pragma unroll
@@ -726,6 +797,9 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             for (int L = 0; L < 2; ++L) { vself[L] = vself_next[L]; wself[L] = wself_next[L]; }
         }
     }
+#if OPESCI_PACE > 0
+    if (A.pace && tid == 0) A.pace[((size_t)chunk * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = 0x7fffffff;
+#endif
 }
 
 // All six shell slabs in one launch: blockIdx.x is a flat block index over the boxes.

@@ -131,6 +131,7 @@ struct Run {
     void *d_recv_out = nullptr;         // [ntsteps][4][n_receivers] real_t
     float *d_src = nullptr;             // [3][src_nt]
     int *d_step = nullptr;              // time-step counter on the device
+    int *d_pace = nullptr;              // fused kernel, OPESCI_PACE: current plane of every tile [chunk][ytile][ztile]
     long long src_cell = -1;
     bool host_pinned = false;
     double *d_tables = nullptr;
@@ -732,6 +733,31 @@ struct Stepper {
             // z columns [M, zend) are covered by tiles; tile bx stores [bx*CZ + M - ZS, bx*CZ + M - ZS + CZ)
             const int zend = R.zstrip > 0 ? R.zstrip : Md.G.dim[2] - M;
             dim3 grid(K::ztiles(zend + M), (Md.G.dim[1] - 2 * M + K::CY - 1) / K::CY, count);
+            A.cluster_sync = 0;
+            A.pace = nullptr;
+#if OPESCI_PACE > 0
+            if (mode == 0) {
+                // every tile publishes the plane it is at; a tile more than OPESCI_PACE planes ahead of a running
+                // y-neighbour waits, so the rows both of them read are still in L2 when the second one arrives
+                const size_t nb = (size_t)grid.x * grid.y * OPESCI_MAX_CHUNKS * sizeof(int);   // allocated by setup_fused
+                cudaMemsetAsync(R.d_pace, 0xFF, nb, st);   // -1: not started
+                A.pace = R.d_pace;
+            }
+#endif
+#if OPESCI_CLUSTER_Z > 1
+            if (mode == 0 && grid.x % OPESCI_CLUSTER_Z == 0) {
+                A.cluster_sync = 1;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = grid; cfg.blockDim = dim3(K::THREADS); cfg.dynamicSmemBytes = K::SMEM; cfg.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = OPESCI_CLUSTER_Z; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                cudaError_t e = Md.p.hetero ? cudaLaunchKernelEx(&cfg, fused_step<SO, ARITH, true>, R.tmap[0], R.tmap[1], R.tmap[2], A)
+                                            : cudaLaunchKernelEx(&cfg, fused_step<SO, ARITH, false>, R.tmap[0], R.tmap[1], R.tmap[2], A);
+                if (e != cudaSuccess && err == cudaSuccess) err = e;
+            } else
+#endif
             if (Md.p.hetero) fused_step<SO, ARITH, true><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
             else fused_step<SO, ARITH, false><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
             check();
@@ -988,6 +1014,9 @@ int setup_fused(Run &R)
         }
         R.overlap = R.box_hi[0] > R.box_lo[0] && R.box_hi[1] > R.box_lo[1] && R.box_hi[2] > R.box_lo[2];
     }
+#if OPESCI_PACE > 0
+    if (!R.d_pace) CUDA_OK(cudaMalloc(&R.d_pace, (size_t)tiles * OPESCI_MAX_CHUNKS * sizeof(int)));
+#endif
     R.fused = true;
     return 0;
 }
@@ -1324,6 +1353,7 @@ void release(Run *R)
     if (R->d_recv_out) cudaFree(R->d_recv_out);
     if (R->d_src) cudaFree(R->d_src);
     if (R->d_step) cudaFree(R->d_step);
+    if (R->d_pace) cudaFree(R->d_pace);
     delete R;
 }
 
