@@ -273,6 +273,9 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 #ifndef OPESCI_PACE
 #define OPESCI_PACE 0   /* > 0: a tile never runs more than this many planes ahead of a running y-neighbour (A/B experiment) */
 #endif
+#ifndef OPESCI_PACE_MAX
+#define OPESCI_PACE_MAX 48
+#endif
 #ifndef OPESCI_CLUSTER_Z
 #define OPESCI_CLUSTER_Z 1   /* > 1: z-adjacent CTAs form a thread-block cluster and march in lockstep (cluster barrier per plane) */
 #endif
@@ -446,7 +449,9 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                         if (by < 0 || by >= (int)gridDim.y) continue;
                         volatile int *pn = pg + dy * (int)gridDim.x;
                         int v = *pn;
-                        while (v >= 0 && v < xs - OPESCI_PACE) { __nanosleep(200); v = *pn; }
+                        // (a neighbour more than OPESCI_PACE_MAX planes behind belongs to a later wave: waiting for it
+                        // would stall this tile for most of its run)
+                        while (v >= 0 && v < xs - OPESCI_PACE && v >= xs - OPESCI_PACE_MAX) { __nanosleep(100); v = *pn; }
                     }
                 }
                 __syncthreads();
