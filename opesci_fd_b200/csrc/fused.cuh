@@ -246,10 +246,30 @@ __device__ __forceinline__ void gstore2(float *p, float a, float b)
 // along y and x is one 8-byte access for both points and the z-windows of both come from three
 // 8-byte loads, which halves the load/store-unit instruction count (the busiest pipe of the
 // one-point-per-thread version, ncu: profiles/r01_fused_v2_ncu_summary.txt).
+// The five stress fields that are published to the shared-memory ring anyway (Txy, Txz, Tyy, Tyz, Tzz) leave the SM as
+// TMA tensor stores straight from their ring slot (one 64 x 12 box per field and plane, issued by one thread) instead of
+// 5 x 512 STG.64: measured 19.9 -> 19.3 ms at 1024^3.  The box is the full tile width, so the two recomputed halo
+// columns on either side are written as well -- with the bits the neighbouring tile writes there (same operands, same
+// operation order).  Tiles whose box would reach outside the interior -- the first tile column, whose halo columns are
+// the ghost cells z < m, and a ragged last column / row -- keep ordinary stores.
+#ifndef OPESCI_TMA_STORE
+#define OPESCI_TMA_STORE 1
+#endif
+struct StoreMaps { CUtensorMap m[5]; };   // Txy, Txz, Tyy, Tyz, Tzz (ring order), box = EZ x CY x 1
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tmap, const void *src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap), "r"(smem_u32(src)), "r"(c0),
+                 "r"(c1), "r"(c2)
+                 : "memory");
+}
 template <int SO, int ARITH, bool HET = false>
 __global__ void __launch_bounds__(FusedCfg<SO / 2>::THREADS, OPESCI_FUSED_MINB)
 fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
-           const __grid_constant__ CUtensorMap tmW, const FusedArgs A)
+           const __grid_constant__ CUtensorMap tmW, const FusedArgs A
+#if OPESCI_TMA_STORE
+           , const __grid_constant__ StoreMaps SMAPS
+#endif
+)
 {
     constexpr int M = SO / 2;
     using K = FusedCfg<M>;
@@ -342,6 +362,10 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     // The recomputed halo ROWS of the tile (a whole warp each) feed only the y-windows of the core rows next to them:
     // Txy, Tyy, Tyz.  Their Txx, Tzz, Txz are never read by anyone, so those warps neither load nor update them.
     const bool halo_row = OPESCI_HALO_SKIP && (ty < M || ty >= M + K::CY);
+    // CTA-uniform: tiles whose whole 64 x 12 store box lies inside the interior (not the first tile column, whose halo
+    // columns are ghost cells; not a ragged last column / row)
+    const bool tma_st = OPESCI_TMA_STORE && !OPESCI_SPLIT_BARRIER && blockIdx.x > 0 &&
+                        (int)blockIdx.x * K::CZ - K::ZS + K::EZ <= G.dim[2] - M && (int)blockIdx.y * K::CY + M + K::CY <= G.dim[1] - M;
     const int xv_lo = max(xa, 2 * M + 1), xv_hi = min(xb, G.dim[0] - 2 * M - 1);
     const long long pyz = (long long)ye * G.s[1] + ze;
     const long long lv0 = (long long)A.t0 * G.level, lv1 = (long long)A.t1 * G.level;
@@ -619,10 +643,12 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             if (xs >= xa && xs < xb) {
                 if (st2) {
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) gstore2(gT1[k] + px, tn[0][k], tn[1][k]);
+                    for (int k = 0; k < 6; ++k)
+                        if (k == 0 || !tma_st) gstore2(gT1[k] + px, tn[0][k], tn[1][k]);
                 } else {
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
+                        if (k != 0 && tma_st) continue;
                         if (st_yz[0]) gstore(gT1[k] + px, tn[0][k]);
                         if (st_yz[1]) gstore(gT1[k] + px + 1, tn[1][k]);
                     }
@@ -678,7 +704,25 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                 const int rp = (r + RD - 1) % RD;
                 const int pU = xs - 1 - M + RD, pVW = xs - M + RD;
 #else
+#if OPESCI_TMA_STORE
+            if (tma_st) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the publish above -> visible to the TMA engine
+                // the slot published NEXT plane was stored from three planes ago: that store must have read it before
+                // anybody passes the barrier below
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+            }
+#endif
             __syncthreads();
+#if OPESCI_TMA_STORE
+            if (tma_st && tid == 0 && xs >= xa && xs < xb) {
+                const T *s0 = sring + (xs & (K::SR - 1)) * ST + M * K::EZ;      // first core row of the slot
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+                    tma_store_3d(&SMAPS.m[k], s0 + k * K::SR * ST, (int)blockIdx.x * K::CZ - K::ZS, (int)blockIdx.y * K::CY + M,
+                                 A.t1 * G.dim[0] + xs);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+#endif
             // ---- the oldest planes (window entry 0, slot r) are dead: refill their slots
             if (tid == 0) {
                 const int rp = r;
@@ -802,6 +846,9 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             for (int L = 0; L < 2; ++L) { vself[L] = vself_next[L]; wself[L] = wself_next[L]; }
         }
     }
+#if OPESCI_TMA_STORE
+    if (tma_st && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
 #if OPESCI_PACE > 0
     if (A.pace && tid == 0) A.pace[((size_t)chunk * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = 0x7fffffff;
 #endif

@@ -140,6 +140,9 @@ struct Run {
     size_t host_bytes_per_field = 0;
     bool fused = false;             // fused stress+velocity kernel in use
     CUtensorMap tmap[3];            // U, V, W (both time levels; level selected through the x coordinate)
+#if OPESCI_TMA_STORE
+    StoreMaps smaps;                // TMA stores of Txy, Txz, Tyy, Tyz, Tzz from the stress ring (fused.cuh)
+#endif
     bool tiled = false;             // TMA-tiled two-pass kernels in use (tiled.cuh: so >= 6, fp64)
     CUtensorMap tmap9[OPESCI_MAX_FIELDS];   // all nine fields, box = TileCfg tile
     int nchunks = 1;                // x-chunks of the fused kernel: chunk c covers planes [xs[c], xs[c+1])
@@ -753,13 +756,23 @@ struct Stepper {
                 at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = OPESCI_CLUSTER_Z; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 cfg.attrs = at; cfg.numAttrs = 1;
+#if OPESCI_TMA_STORE
+                cudaError_t e = Md.p.hetero ? cudaLaunchKernelEx(&cfg, fused_step<SO, ARITH, true>, R.tmap[0], R.tmap[1], R.tmap[2], A, R.smaps)
+                                            : cudaLaunchKernelEx(&cfg, fused_step<SO, ARITH, false>, R.tmap[0], R.tmap[1], R.tmap[2], A, R.smaps);
+#else
                 cudaError_t e = Md.p.hetero ? cudaLaunchKernelEx(&cfg, fused_step<SO, ARITH, true>, R.tmap[0], R.tmap[1], R.tmap[2], A)
                                             : cudaLaunchKernelEx(&cfg, fused_step<SO, ARITH, false>, R.tmap[0], R.tmap[1], R.tmap[2], A);
+#endif
                 if (e != cudaSuccess && err == cudaSuccess) err = e;
             } else
 #endif
+#if OPESCI_TMA_STORE
+            if (Md.p.hetero) fused_step<SO, ARITH, true><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A, R.smaps);
+            else fused_step<SO, ARITH, false><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A, R.smaps);
+#else
             if (Md.p.hetero) fused_step<SO, ARITH, true><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
             else fused_step<SO, ARITH, false><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
+#endif
             check();
             if (R.zstrip > 0) {
                 // A few z columns are left over after the last full tile (1025 = 17 x 60 + 5 at 1024^3): a whole row of
@@ -930,6 +943,23 @@ int setup_fused(Run &R)
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rc != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed");
     }
+#if OPESCI_TMA_STORE
+    {
+        // ring order of the published fields: Txy, Txz, Tyy, Tyz, Tzz
+        const int ring_field[5] = {F_TXY, F_TXZ, F_TYY, F_TYZ, F_TZZ};
+        for (int k = 0; k < 5; ++k) {
+            // extents stop at dim - m: box elements beyond the last interior row / column are not written
+            cuuint64_t gdim[3] = {(cuuint64_t)(p.dim[2] - m), (cuuint64_t)(p.dim[1] - m), (cuuint64_t)M.G.dim[0] * p.nlevels};
+            cuuint64_t gstride[2] = {(cuuint64_t)M.G.s[1] * 4, (cuuint64_t)M.G.s[0] * 4};
+            cuuint32_t box[3] = {(cuuint32_t)OPESCI_FUSED_EZ, (cuuint32_t)(OPESCI_FUSED_EY - 2 * m), 1};
+            cuuint32_t estr[3] = {1, 1, 1};
+            if (encode(&R.smaps.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, R.dev[ring_field[k]], gdim, gstride, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return fail("cuTensorMapEncodeTiled failed (store maps)");
+        }
+    }
+#endif
     if (m == 1) { if (set_fused_attr<1, OPESCI_ARITH_REFERENCE>() || set_fused_attr<1, OPESCI_ARITH_FAST>()) return 1; }
     else { if (set_fused_attr<2, OPESCI_ARITH_REFERENCE>() || set_fused_attr<2, OPESCI_ARITH_FAST>()) return 1; }
     // x-chunks: enough CTAs to fill the machine in whole waves, few enough to keep the 2m-plane
