@@ -128,8 +128,10 @@ class Grid(object):
         if self.src_lib is None:
             self.compile(filename, compiler=compiler, shared=True)
         self._load_library(src_lib=self.src_lib)
-        print("Executing on %s (host threads requested: %d, affinity=%s)"
-              % ("B200 (CUDA)" if self._library.opesci_b200_is_cuda() else "CPU oracle", nthreads, affinity))
+        if not self._library.opesci_b200_is_cuda():
+            # execute() is the product path: only the CUDA library may serve it (no CPU fallback)
+            raise RuntimeError("%s is not the CUDA library; Grid.execute() runs on the B200 only" % self.src_lib)
+        print("Executing on B200 (CUDA) (host threads requested: %d, affinity=%s)" % (nthreads, affinity))
         self.run()
         if self.profiling:
             print("B200:: time loop: %f (sec)" % self._arg_profiling.g_rtime)

@@ -187,3 +187,17 @@ def test_generate_writes_model_description(tmp_path):
     desc = json.loads(out.read_text())
     assert desc["dim"] == [17, 17, 17] and desc["so"] == 4 and desc["free_surface"] == abi.FS_LEVANDER
     assert abs(desc["c_stress_normal"][0][0][0] - 9.0 / 8 * 0.002 * 12 * 1.0) < 1e-6
+
+
+def test_execute_refuses_a_non_cuda_library(tmp_path):
+    # Grid.execute() is the product entry point (reference: opesci/grid.py:85-130): handing it the CPU
+    # oracle must fail instead of silently running on the host
+    import eigenwave3d as drv
+    import __graft_entry__ as ge
+    g = drv.eigenwave3d((1.0, 1.0, 1.0), (12, 12, 12), 0.002, 0.01, accuracy_order=[2, 4, 4, 4], verbose=False)
+    g.src_lib = ge.build_oracle()
+    with pytest.raises(RuntimeError, match="not the CUDA library"):
+        g.execute(str(tmp_path / "m.json"))
+    g.src_lib = str(tmp_path / "missing.so")
+    with pytest.raises(Exception, match="no CPU fallback"):
+        g.execute(str(tmp_path / "m.json"))
