@@ -158,8 +158,12 @@ def test_unsupported_models_raise():
 
 def test_cuda_library_exports_the_abi(cuda_lib):
     # loading + symbol lookup only: no compute without a GPU
-    hdr = open(os.path.join(ROOT, "include", "opesci_b200.h")).read()
+    # every entry point any header under include/ declares
+    hdr = "".join(open(os.path.join(ROOT, "include", h)).read()
+                  for h in sorted(os.listdir(os.path.join(ROOT, "include"))) if h.endswith(".h"))
+    hdr = re.sub(r"/\*.*?\*/|//[^\n]*", "", hdr, flags=re.S)             # prose in comments is not a declaration
     declared = set(re.findall(r"\b(opesci_\w+)\s*\(", hdr))
+    declared -= set(re.findall(r"static\s+inline[^(]*?\b(opesci_\w+)\s*\(", hdr))   # header-only geometry helpers
     assert declared >= {"opesci_execute", "opesci_convergence", "opesci_free", "opesci_b200_configure"}
     for sym in declared:
         assert hasattr(cuda_lib, sym), "libopesci_b200.so does not export %s" % sym
