@@ -2,6 +2,8 @@
 
 TEST INFRASTRUCTURE.  Launched by torch.distributed.run; writes the rank's local slab of every field
 (both time levels), its slab geometry and its L2 partial norms to <outdir>/rank<r>.npz.
+argv[2] is one configuration (JSON object) or a JSON list of them: job i of a list writes to
+<outdir>/job<i>/, so that one rendezvous serves a whole batch of cases.
 """
 import ctypes
 import json
@@ -23,7 +25,7 @@ EXCHANGE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, c
 
 
 def main():
-    outdir, cfg = sys.argv[1], json.loads(sys.argv[2])
+    outdir, cfgs = sys.argv[1], json.loads(sys.argv[2])
     use_cuda = len(sys.argv) > 3 and sys.argv[3] == "cuda"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -61,6 +63,21 @@ def main():
         lib.opesci_oracle_set_exchange.argtypes = [EXCHANGE_FN, ctypes.c_void_p]
         lib.opesci_oracle_set_exchange(cb, None)
 
+    if isinstance(cfgs, dict):
+        run_job(outdir, cfgs, lib, rank, world, use_cuda)
+    else:
+        for i, cfg in enumerate(cfgs):
+            job_dir = os.path.join(outdir, "job%d" % i)
+            os.makedirs(job_dir, exist_ok=True)
+            run_job(job_dir, cfg, lib, rank, world, use_cuda)
+            dist.barrier()
+    if use_cuda:
+        lib.opesci_b200_comm_finalize()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_job(outdir, cfg, lib, rank, world, use_cuda):
     flags = os.environ.get("OPESCI_TEST_FLAGS")
     grid = make_grid(cfg, flags=int(flags) if (flags and use_cuda) else None)
     if cfg["kind"] == "eigenwave3d_read":
@@ -109,10 +126,6 @@ def main():
     np.savez(os.path.join(outdir, "rank%d.npz" % rank), fields=np.stack(fields), L0=L0, L1=L1, own_lo=own_lo, own_hi=own_hi, l2=l2,
              receivers=rec if rec is not None else np.zeros(0))
     grid.free()
-    if use_cuda:
-        lib.opesci_b200_comm_finalize()
-    dist.barrier()
-    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

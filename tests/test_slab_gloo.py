@@ -24,27 +24,56 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize("world,so,kind", [(2, 4, "eigenwave3d"), (3, 4, "eigenwave3d"), (2, 2, "eigenwave3d"),
-                                           (2, 4, "eigenwave3d_read"), (2, 4, "simplewave3d"), (3, 8, "simplewave3d"),
-                                           (2, 8, "eigenwave3d"), (2, 12, "eigenwave3d"), (2, 6, "eigenwave3d_read")])
-def test_slab_decomposition_is_bit_exact(world, so, kind, oracle_lib, tmp_path):
-    cfg = dict(kind=kind, so=so, grid_size=[30 * world, 11, 9], dt=0.002, steps=11, double=False,
-               domain=[1.0 * world, 0.9, 0.8], rho=1.2, vp=1.6, vs=0.8, seed=11)
-    single = make_grid(cfg)
+CASES = [(2, 4, "eigenwave3d"), (3, 4, "eigenwave3d"), (2, 2, "eigenwave3d"),
+         (2, 4, "eigenwave3d_read"), (2, 4, "simplewave3d"), (3, 8, "simplewave3d"),
+         (2, 8, "eigenwave3d"), (2, 12, "eigenwave3d"), (2, 6, "eigenwave3d_read")]
+HOOKS = dict(receivers=[[0.3, 0.4, 0.4], [1.2, 0.5, 0.3], [1.9, 0.2, 0.6], [1.0, 0.45, 0.4]], source=[1.0, 0.45, 0.4],
+             wavelet=[0.0, 0.01, 0.03, 0.01, -0.02, 0.0])
+
+
+def _case_cfg(world, so, kind):
+    return dict(kind=kind, so=so, grid_size=[30 * world, 11, 9], dt=0.002, steps=11, double=False,
+                domain=[1.0 * world, 0.9, 0.8], rho=1.2, vp=1.6, vs=0.8, seed=11)
+
+
+def _hooks_cfg():
+    return dict(kind="eigenwave3d", so=4, grid_size=[60, 11, 9], dt=0.002, steps=11, double=False,
+                domain=[2.0, 0.9, 0.8], rho=1.2, vp=1.6, vs=0.8, hooks=HOOKS)
+
+
+@pytest.fixture(scope="module")
+def slab_runs(oracle_lib, tmp_path_factory):
+    """One torch.distributed.run per world size serves every case of that size (a rendezvous plus two or three
+    `import torch` cost more than all the oracle runs together).  -> {case key: directory with rank<r>.npz}"""
+    jobs = {}
+    for world, so, kind in CASES:
+        jobs.setdefault(world, []).append(((world, so, kind), _case_cfg(world, so, kind)))
+    jobs[2].append(("hooks", _hooks_cfg()))
+    where = {}
+    for world, batch in sorted(jobs.items()):
+        out_root = tmp_path_factory.mktemp("slabs_w%d" % world)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+               os.path.join(ROOT, "tests", "slab_worker.py"), str(out_root), json.dumps([cfg for _, cfg in batch])]
+        out = subprocess.run(cmd, env=dict(os.environ, OMP_NUM_THREADS="2"), capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+        for i, (key, _) in enumerate(batch):
+            where[key] = os.path.join(str(out_root), "job%d" % i)
+    return where
+
+
+@pytest.mark.parametrize("world,so,kind", CASES)
+def test_slab_decomposition_is_bit_exact(world, so, kind, oracle_lib, slab_runs):
+    single = make_grid(_case_cfg(world, so, kind))
     single.run(library=oracle_lib)
     ref = fields_of(single)
     ref_l2 = np.array(single.convergence_f64())
     single.free()
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "slab_worker.py"), str(tmp_path), json.dumps(cfg)]
-    env = dict(os.environ, OMP_NUM_THREADS="2")
-    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    outdir = slab_runs[(world, so, kind)]
     sums = np.zeros(ref.shape[0])
     covered = 0
     for r in range(world):
-        z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        z = np.load(os.path.join(outdir, "rank%d.npz" % r))
         L0, own_lo, own_hi = int(z["L0"]), int(z["own_lo"]), int(z["own_hi"])
         mine = z["fields"][:, :, own_lo - L0:own_hi - L0]
         want = ref[:, :, own_lo:own_hi]
@@ -55,28 +84,20 @@ def test_slab_decomposition_is_bit_exact(world, so, kind, oracle_lib, tmp_path):
     np.testing.assert_allclose(np.sqrt(sums), ref_l2, rtol=1e-12)
 
 
-def test_slab_point_source_and_receivers(oracle_lib, tmp_path):
+def test_slab_point_source_and_receivers(oracle_lib, slab_runs):
     """Source and receivers with slabs: every rank handles the cells on planes it owns, so the per-rank receiver
     traces add up to the single-domain traces and the fields stay bit-identical."""
-    hooks = dict(receivers=[[0.3, 0.4, 0.4], [1.2, 0.5, 0.3], [1.9, 0.2, 0.6], [1.0, 0.45, 0.4]], source=[1.0, 0.45, 0.4],
-                 wavelet=[0.0, 0.01, 0.03, 0.01, -0.02, 0.0])
-    cfg = dict(kind="eigenwave3d", so=4, grid_size=[60, 11, 9], dt=0.002, steps=11, double=False,
-               domain=[2.0, 0.9, 0.8], rho=1.2, vp=1.6, vs=0.8, hooks=hooks)
-    single = make_grid(cfg)
-    single.set_receivers(hooks["receivers"])
-    single.set_source(hooks["source"], np.array(hooks["wavelet"], dtype=np.float32))
+    single = make_grid(_hooks_cfg())
+    single.set_receivers(HOOKS["receivers"])
+    single.set_source(HOOKS["source"], np.array(HOOKS["wavelet"], dtype=np.float32))
     single.run(library=oracle_lib)
     ref = fields_of(single)
     ref_rec = single.receiver_data().copy()
     single.free()
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "slab_worker.py"), str(tmp_path), json.dumps(cfg)]
-    out = subprocess.run(cmd, env=dict(os.environ, OMP_NUM_THREADS="2"), capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    outdir = slab_runs["hooks"]
     total = np.zeros_like(ref_rec)
     for r in range(2):
-        z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        z = np.load(os.path.join(outdir, "rank%d.npz" % r))
         L0, own_lo, own_hi = int(z["L0"]), int(z["own_lo"]), int(z["own_hi"])
         mine = np.ascontiguousarray(z["fields"][:, :, own_lo - L0:own_hi - L0])
         assert int((bits(mine) != bits(np.ascontiguousarray(ref[:, :, own_lo:own_hi]))).sum()) == 0, "rank %d" % r
