@@ -126,9 +126,13 @@ enum {
     OPESCI_HOST_MIRROR_MASK = 0x30,
     OPESCI_NO_CUDA_GRAPH = 1 << 8,
     OPESCI_FORCE_UNFUSED = 1 << 9,      /* two-pass stress / velocity kernels (diagnostic) */
-    OPESCI_FORCE_TILED = 1 << 11,       /* TMA-tiled two-pass kernels also where the fused kernel applies (diagnostic) */
-    OPESCI_OVERLAP = 1 << 10            /* experimental: run the ghost loops of step n-1 concurrently with the tiles of
-                                         * step n that cannot see them (bit-identical; no gain measured on B200) */
+    OPESCI_FORCE_TILED = 1 << 11,
+    OPESCI_L2_REFERENCE = 1 << 12,      /* opesci_convergence accumulates like the reference: serially, in real_t, in loop
+                                         * order (staggeredgrid.py:916,935) -- reproduces its printed digits; a serial
+                                         * chain by definition (seconds at 256^3), single rank only.  Default: double tree */       /* TMA-tiled two-pass kernels also where the fused kernel applies (diagnostic) */
+    OPESCI_OVERLAP = 1 << 10            /* accepted and ignored.  Round 1 had an experimental schedule behind it (ghost loops
+                                         * of step n-1 concurrent with independent tiles of step n): no gain measured on
+                                         * B200, and it raced with the point source, so the path was removed */
 };
 
 typedef struct OpesciB200Params {
@@ -255,6 +259,13 @@ int opesci_b200_comm_finalize(void);
 /* the planes [L0,L1) of global dim1 that rank `rank` of `nranks` stores (its slab plus halos): what a
  * heterogeneous run has to supply in rho/vp/vs (media_plane0 = L0, media_nplanes = L1-L0); staggered elastic model */
 int opesci_b200_slab_range(int rank, int nranks, int gdim1, int so, int *L0, int *L1);
+/* Loopback slabs: `nranks` logical ranks of the configured model (configured for the WHOLE domain, slab_nranks <= 1)
+ * run concurrently on the CURRENT device, one host thread per rank, each through exactly the schedule a real rank runs
+ * (x-chunk table, overlap of the halo exchange with the middle chunks, ghost loops, shell); only the transport of the
+ * halo planes differs -- device-to-device copies instead of ncclSend / ncclRecv.  grids[r] receives rank r's arrays
+ * (planes [L0,L1) of opesci_b200_slab_range, all time levels; host or device per the HOST_MIRROR flag); free each with
+ * opesci_free.  Proof of slab exactness on a one-GPU box: the owned planes must equal the single-domain run bit for bit. */
+int opesci_b200_execute_loopback(int nranks, OpesciGrid *grids);
 /* 1 if this library was built with the CUDA kernels (0 for the CPU oracle build) */
 int opesci_b200_is_cuda(void);
 

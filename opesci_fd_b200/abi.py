@@ -26,10 +26,12 @@ ARITH_REFERENCE = 0
 ARITH_FAST = 1
 HOST_MIRROR_FULL = 0 << 4
 HOST_MIRROR_NONE = 1 << 4
+HOST_MIRROR_MASK = 0x30
 NO_CUDA_GRAPH = 1 << 8
 FORCE_UNFUSED = 1 << 9
 OVERLAP = 1 << 10
 FORCE_TILED = 1 << 11
+L2_REFERENCE = 1 << 12
 
 FS_NONE, FS_LEVANDER, FS_ROBERTSSON = 0, 1, 2
 
@@ -103,6 +105,7 @@ EXPORTED_SYMBOLS = [
     "opesci_b200_is_cuda", "opesci_b200_time_kernels",
     "opesci_b200_comm_unique_id", "opesci_b200_comm_init", "opesci_b200_comm_finalize",
     "opesci_b200_reserve_host", "opesci_b200_release_host", "opesci_b200_slab_range",
+    "opesci_b200_execute_loopback",
 ]
 # include/opesci_io.h (model input / field output around the path)
 IO_SYMBOLS = [
@@ -156,6 +159,9 @@ def bind(lib):
         lib.opesci_b200_slab_range.restype = ctypes.c_int
     lib.opesci_b200_is_cuda.argtypes = []
     lib.opesci_b200_is_cuda.restype = ctypes.c_int
+    if hasattr(lib, "opesci_b200_execute_loopback"):
+        lib.opesci_b200_execute_loopback.argtypes = [ctypes.c_int, POINTER(OpesciGrid)]
+        lib.opesci_b200_execute_loopback.restype = ctypes.c_int
     if hasattr(lib, "opesci_b200_set_output"):
         bind_io(lib)
     return lib
@@ -202,6 +208,16 @@ def load_library(path=None):
     Mirrors Grid._load_library (reference: opesci/grid.py:35-42): a load failure raises.
     """
     libname = path or CUDA_LIBRARY
+    if "OPESCI_NCCL_LIB" not in os.environ:
+        # slabs: the C library dlopens NCCL by name; point it at the copy shipped with the nvidia-nccl wheel
+        # (the one torch uses) when there is one, found relative to the interpreter -- no fixed path
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["OPESCI_NCCL_LIB"] = cand
+                break
     if not os.path.exists(libname):
         raise Exception("Failed to load %s: file not found (build it with "
                         "`python -c 'import __graft_entry__ as g; g.build()'`); "

@@ -148,7 +148,10 @@ template <int M> struct FusedCfg {
 #define OPESCI_FUSED_ALIGN 0   /* measured on B200: 20.2 vs 19.9 ms -- whole-sector stores, but 19 tile columns of 56 instead of 18 of 60 and 5 % more halo re-reads */
 #endif
     static constexpr int ZS = (OPESCI_FUSED_ALIGN && M == 2) ? 2 : 0;
-    static constexpr int CZ = ZS ? (EZ - 2 * M) / 8 * 8 : (EZ - 2 * M) / 4 * 4, CY = EY - 2 * M;
+#ifndef OPESCI_EXP_CY_EXTRA
+#define OPESCI_EXP_CY_EXTRA 0   /* TIMING PROBE ONLY (wrong results): tile rows advance by EY - 2M + this */
+#endif
+    static constexpr int CZ = ZS ? (EZ - 2 * M) / 8 * 8 : (EZ - 2 * M) / 4 * 4, CY = EY - 2 * M + OPESCI_EXP_CY_EXTRA;
     static constexpr int OFFZ = (M + ZS + 3) / 4 * 4;
     static constexpr int VZ = (EZ + M + OFFZ - ZS + 3) / 4 * 4, VY = EY + 2 * M;   // velocity tile delivered by TMA
     // number of tiles along z for an array of dim3 = dim
@@ -177,13 +180,8 @@ struct FusedArgs {
 #define OPESCI_MAX_CHUNKS 20
     int xs[OPESCI_MAX_CHUNKS + 1];   // x-chunk c covers planes [xs[c], xs[c+1]); blockIdx.z + chunk0 selects the chunk
     int chunk0;
-    // Tile subset of this launch.  The tiles inside the box [box_lo, box_hi) (tile_y, tile_z, chunk)
-    // neither read nor write any cell the ghost-cell loops / shell update of the PREVIOUS step touch,
-    // so they can run concurrently with those loops; the remaining tiles run afterwards.
     int *pace;        // OPESCI_PACE: progress of every tile (plane index; -1 not started; INT_MAX done), else null
     int cluster_sync; // launched as clusters of OPESCI_CLUSTER_Z z-adjacent CTAs (A/B experiment)
-    int mode;         // 0: every tile, 1: only tiles inside the box, 2: only tiles outside the box
-    int box_lo[3], box_hi[3];
 };
 
 // six consecutive floats p[-2..3] as three aligned 8-byte loads (p must be 8-byte aligned)
@@ -301,11 +299,6 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 #endif
     const GridGeom &G = A.G;
     const int tid = threadIdx.x;
-    if (A.mode != 0) {
-        const bool inside = (int)blockIdx.y >= A.box_lo[0] && (int)blockIdx.y < A.box_hi[0] && (int)blockIdx.x >= A.box_lo[1] &&
-                            (int)blockIdx.x < A.box_hi[1] && (int)blockIdx.z + A.chunk0 >= A.box_lo[2] && (int)blockIdx.z + A.chunk0 < A.box_hi[2];
-        if ((A.mode == 1) != inside) return;
-    }
     const int tz = 2 * (tid % (K::EZ / 2)), ty = tid / (K::EZ / 2);          // lane 0 sits at tz, lane 1 at tz+1
     const int ye = blockIdx.y * K::CY + ty, ze = blockIdx.x * K::CZ + tz - K::ZS;   // global coords of lane 0 (ze < 0: outside)
     const int chunk = blockIdx.z + A.chunk0;

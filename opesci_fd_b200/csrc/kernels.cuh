@@ -676,4 +676,59 @@ __global__ void l2_final(const double *__restrict__ partial, size_t n, double *_
     }
 }
 
+// ---- OPESCI_L2_REFERENCE: the reference's own norm arithmetic (opesci/staggeredgrid.py:916,935 / regulargrid.py:676,695):
+// `F_l2 += pow(F[ti][x][y][z] - (solution), 2.0)` with a real_t accumulator, serially in loop order x, y, z.
+// l2_terms evaluates the per-cell terms in parallel (double: the emitted C++ promotes to double and gcc folds
+// pow(e, 2.0) to e*e); l2_serial then performs the reference's additions one by one, rounding the accumulator to real_t
+// after each -- a serial chain by definition, so this path is opt-in and meant for the sizes the reference itself runs.
+template <typename T>
+__global__ void l2_terms(const T *__restrict__ A /* level ti */, GridGeom G, Range3 R, const DevProgram *__restrict__ prog,
+                         double *__restrict__ terms /* [x - lo0][y - lo1][z - lo2] */)
+{
+    __shared__ DevProgram pr;
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    for (int i = tid; i < (int)(sizeof(DevProgram) / 4); i += blockDim.x * blockDim.y)
+        ((int *)&pr)[i] = ((const int *)prog)[i];
+    __syncthreads();
+    const int z = R.lo[2] + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = R.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = R.lo[0] + blockIdx.z;
+    if (z >= R.hi[2] || y >= R.hi[1]) return;
+    const long long cell = (long long)x * G.s[0] + (long long)y * G.s[1] + z;
+    const double e = run_program(pr, x, y, z, (double)A[cell], cell);
+    const size_t ny = R.hi[1] - R.lo[1], nz = R.hi[2] - R.lo[2];
+    terms[((size_t)(x - R.lo[0]) * ny + (y - R.lo[1])) * nz + (z - R.lo[2])] = __dmul_rn(e, e);
+}
+
+struct L2SerialArgs { long long count[OPESCI_MAX_FIELDS]; };
+// one CTA per field: thread 0 adds, the other warps stage the next tile of terms in shared memory
+template <typename T>
+__global__ void __launch_bounds__(256) l2_serial(const double *__restrict__ terms, size_t field_stride, L2SerialArgs N, T *__restrict__ acc)
+{
+    constexpr int TILE = 2048;
+    __shared__ double buf[2][TILE];
+    const int f = blockIdx.x;
+    const long long n = N.count[f];
+    if (n <= 0) return;
+    const double *src = terms + (size_t)f * field_stride;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < TILE && i < n; i += 256) buf[0][i] = src[i];
+    __syncthreads();
+    T a = acc[f];
+    const long long ntiles = (n + TILE - 1) / TILE;
+    for (long long t = 0; t < ntiles; ++t) {
+        const long long base = t * TILE, nextb = base + TILE;
+        if (tid >= 32) {
+            for (long long i = tid - 32; i < TILE && nextb + i < n; i += 224) buf[(t + 1) & 1][i] = src[nextb + i];
+        } else if (tid == 0) {
+            const double *b = buf[t & 1];
+            const int cnt = (int)((n - base) < TILE ? (n - base) : TILE);
+#pragma unroll 8
+            for (int i = 0; i < cnt; ++i) a = (T)__dadd_rn((double)a, b[i]);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) acc[f] = a;
+}
+
 }  // namespace opesci

@@ -12,13 +12,17 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <type_traits>
 #include <vector>
 
 #include <dlfcn.h>
@@ -34,7 +38,7 @@ using namespace opesci;
 
 namespace {
 
-char g_err[1024] = "";
+thread_local char g_err[1024] = "";   // per thread: the loopback ranks run on threads of their own
 int fail(const char *fmt, const char *a = "", const char *b = "")
 {
     snprintf(g_err, sizeof g_err, fmt, a, b);
@@ -75,13 +79,13 @@ int nccl_bind()
     if (g_nccl.GetUniqueId) return 0;
     void *h = dlopen(nullptr, RTLD_NOW);                       // already in the process (torch)?
     if (!h || !dlsym(h, "ncclCommInitRank")) {
-        const char *names[] = {"libnccl.so.2", "libnccl.so",
-                               "/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/lib/libnccl.so.2"};
+        // OPESCI_NCCL_LIB names the library explicitly; otherwise the standard search path decides
+        const char *names[] = {getenv("OPESCI_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
         h = nullptr;
         for (const char *n : names)
-            if ((h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+            if (n && *n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
     }
-    if (!h) return fail("NCCL not found (dlopen libnccl.so.2 failed): %s", dlerror());
+    if (!h) return fail("NCCL not found: set OPESCI_NCCL_LIB or put libnccl.so.2 on the library path (%s)", dlerror());
     g_nccl.handle = h;
 #define BIND(field, sym) *(void **)(&g_nccl.field) = dlsym(h, sym); if (!g_nccl.field) return fail("NCCL symbol missing: %s", sym)
     BIND(GetUniqueId, "ncclGetUniqueId");
@@ -101,6 +105,44 @@ int nccl_bind()
         int r_ = (call);                                                                        \
         if (r_ != ncclSuccess) return fail("NCCL error: %s at %s", g_nccl.GetErrorString(r_), #call); \
     } while (0)
+
+
+// ------------------------------------------------------------------ loopback slabs
+// N logical ranks of one model executed concurrently on ONE device, each by its own host thread running the very same
+// run_model schedule a real rank runs (chunk table, ev_fork / ev_join, exchange on its own stream); only the transport of
+// the halo planes differs: device-to-device copies between the ranks' arrays instead of ncclSend / ncclRecv.
+// Purpose: proof of slab exactness on a single-GPU box (opesci_b200_execute_loopback, tests/test_gpu_loopback.py).
+struct Run;
+struct HostBarrier {
+    std::mutex mu;
+    std::condition_variable cv;
+    int n = 0, waiting = 0;
+    unsigned long long gen = 0;
+    bool aborted = false;
+    // returns true if a peer gave up (the caller must fail too instead of waiting for ever)
+    bool wait()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        if (aborted) return true;
+        const unsigned long long g = gen;
+        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); return false; }
+        cv.wait(lk, [&] { return gen != g || aborted; });
+        return aborted;
+    }
+    void abort()
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        aborted = true;
+        cv.notify_all();
+    }
+};
+struct Loopback {
+    int nranks = 0;
+    std::vector<Run *> runs;
+    std::vector<cudaEvent_t> done, xdone;
+    HostBarrier barrier;
+};
+thread_local Loopback *tl_loop = nullptr;
 
 
 struct Model {
@@ -149,8 +191,6 @@ struct Run {
     int xs[OPESCI_MAX_CHUNKS + 1] = {};
     int zstrip = 0;                 // > 0: the fused kernel covers z < zstrip only; the thin strip [zstrip, dim-m) is done per point
     int mid0 = 0, mid1 = 0;         // slabs: chunks [mid0, mid1) read no halo plane (they overlap the halo exchange)
-    bool overlap = false;           // ghost loops of step n-1 run concurrently with the independent tiles of step n
-    int box_lo[3] = {0, 0, 0}, box_hi[3] = {0, 0, 0};   // independent tiles (tile_y, tile_z, chunk)
 };
 std::map<void *, Run *> g_runs;
 std::mutex g_mu;
@@ -162,9 +202,19 @@ long long g_launches = 0;
 // The reference ABI hands back host arrays.  Page-locking 80 GB costs tens of seconds, far more than
 // the copy itself, so result arrays come from a process-wide pool of pinned blocks that survives
 // opesci_free (opesci_b200_reserve_host pre-fills it, opesci_b200_release_host frees it).
-struct HostBlock { void *ptr; size_t bytes; bool in_use; bool pinned; };
+// Blocks reserved explicitly (opesci_b200_reserve_host) stay until opesci_b200_release_host; blocks the pool had to
+// allocate on demand are kept after opesci_free only while the idle ones add up to at most OPESCI_HOST_POOL_IDLE_MB
+// (default 1024 MiB), so a caller that never heard of the pool -- the reference front end -- does not keep a whole
+// run's worth of page-locked memory behind.
+struct HostBlock { void *ptr; size_t bytes; bool in_use; bool pinned; bool reserved; };
 std::vector<HostBlock> g_pool;
 std::mutex g_pool_mu;
+bool g_pool_reserving = false;
+size_t pool_idle_cap()
+{
+    const char *e = getenv("OPESCI_HOST_POOL_IDLE_MB");
+    return (size_t)(e && *e ? strtoull(e, nullptr, 10) : 1024ull) << 20;
+}
 
 void *pool_alloc(size_t bytes, bool *pinned)
 {
@@ -173,7 +223,7 @@ void *pool_alloc(size_t bytes, bool *pinned)
     for (int i = 0; i < (int)g_pool.size(); ++i)
         if (!g_pool[i].in_use && g_pool[i].bytes >= bytes && (best < 0 || g_pool[i].bytes < g_pool[best].bytes)) best = i;
     if (best >= 0) { g_pool[best].in_use = true; *pinned = g_pool[best].pinned; return g_pool[best].ptr; }
-    HostBlock b{nullptr, bytes, true, true};
+    HostBlock b{nullptr, bytes, true, true, g_pool_reserving};
     if (cudaMallocHost(&b.ptr, bytes) != cudaSuccess) {
         cudaGetLastError();
         b.pinned = false;
@@ -188,6 +238,22 @@ void pool_release(void *ptr)
     std::lock_guard<std::mutex> lk(g_pool_mu);
     for (auto &b : g_pool)
         if (b.ptr == ptr) b.in_use = false;
+    // trim: free idle on-demand blocks, largest first, until they fit under the cap
+    const size_t cap = pool_idle_cap();
+    for (;;) {
+        size_t idle = 0;
+        int big = -1;
+        for (int i = 0; i < (int)g_pool.size(); ++i) {
+            const HostBlock &b = g_pool[i];
+            if (b.in_use || b.reserved) continue;
+            idle += b.bytes;
+            if (big < 0 || b.bytes > g_pool[big].bytes) big = i;
+        }
+        if (idle <= cap || big < 0) break;
+        if (g_pool[big].pinned) cudaFreeHost(g_pool[big].ptr);
+        else free(g_pool[big].ptr);
+        g_pool.erase(g_pool.begin() + big);
+    }
 }
 
 // ------------------------------------------------------------------ model construction
@@ -719,7 +785,7 @@ struct Stepper {
     }
 
     // fused stress+velocity launch (fused.cuh); only instantiated for so <= 4, fp32
-    template <int SO, typename T, int ARITH> void fused(int t0, int t1, int mode = 0, int chunk0 = 0, int count = -1)
+    template <int SO, typename T, int ARITH> void fused(int t0, int t1, int chunk0 = 0, int count = -1)
     {
         if constexpr (SO <= 4 && sizeof(T) == 4) {
             constexpr int M = SO / 2;
@@ -731,15 +797,13 @@ struct Stepper {
             A.chunk0 = chunk0;
             if (count < 0) count = R.nchunks - chunk0;
             if (count <= 0) return;
-            A.mode = mode;
-            for (int k = 0; k < 3; ++k) { A.box_lo[k] = R.box_lo[k]; A.box_hi[k] = R.box_hi[k]; }
             // z columns [M, zend) are covered by tiles; tile bx stores [bx*CZ + M - ZS, bx*CZ + M - ZS + CZ)
             const int zend = R.zstrip > 0 ? R.zstrip : Md.G.dim[2] - M;
             dim3 grid(K::ztiles(zend + M), (Md.G.dim[1] - 2 * M + K::CY - 1) / K::CY, count);
             A.cluster_sync = 0;
             A.pace = nullptr;
 #if OPESCI_PACE > 0
-            if (mode == 0) {
+            {
                 // every tile publishes the plane it is at; a tile more than OPESCI_PACE planes ahead of a running
                 // y-neighbour waits, so the rows both of them read are still in L2 when the second one arrives
                 const size_t nb = (size_t)grid.x * grid.y * OPESCI_MAX_CHUNKS * sizeof(int);   // allocated by setup_fused
@@ -748,7 +812,7 @@ struct Stepper {
             }
 #endif
 #if OPESCI_CLUSTER_Z > 1
-            if (mode == 0 && grid.x % OPESCI_CLUSTER_Z == 0) {
+            if (grid.x % OPESCI_CLUSTER_Z == 0) {
                 A.cluster_sync = 1;
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = grid; cfg.blockDim = dim3(K::THREADS); cfg.dynamicSmemBytes = K::SMEM; cfg.stream = st;
@@ -902,8 +966,24 @@ int setup_tiled(Run &R)
     if (p.kind != OPESCI_KIND_STAGGERED_ELASTIC || R.fused || (p.flags & OPESCI_FORCE_UNFUSED)) return 0;
     EncodeTiledFn encode = get_encode();
     if (!encode) return fail("cuTensorMapEncodeTiled not available from the driver");
-    const int esz = p.is_double ? 8 : 4, al = 16 / esz;
-    const int VY = 8 + 2 * M.m, VZ = (32 + 2 * M.m + al - 1) / al * al;   // TileCfg<M,T>
+    const int esz = p.is_double ? 8 : 4;
+    // box = the tile the kernels expect (TileCfg<M,T>::VY x VZ): read from the same constexprs the kernels use, so the
+    // tensor-map box and the kernels' expect_tx byte count cannot drift apart
+    int VY = 0, VZ = 0;
+    auto pick = [&](auto mtag) {
+        constexpr int MM = decltype(mtag)::value;
+        if (p.is_double) { VY = TileCfg<MM, double>::VY; VZ = TileCfg<MM, double>::VZ; }
+        else { VY = TileCfg<MM, float>::VY; VZ = TileCfg<MM, float>::VZ; }
+    };
+    switch (M.m) {
+    case 1: pick(std::integral_constant<int, 1>()); break;
+    case 2: pick(std::integral_constant<int, 2>()); break;
+    case 3: pick(std::integral_constant<int, 3>()); break;
+    case 4: pick(std::integral_constant<int, 4>()); break;
+    case 5: pick(std::integral_constant<int, 5>()); break;
+    case 6: pick(std::integral_constant<int, 6>()); break;
+    default: return fail("setup_tiled: unsupported margin");
+    }
     for (int f = 0; f < 9; ++f) {
         cuuint64_t gdim[3] = {(cuuint64_t)p.dim[2], (cuuint64_t)p.dim[1], (cuuint64_t)M.G.dim[0] * p.nlevels};
         cuuint64_t gstride[2] = {(cuuint64_t)M.G.s[1] * esz, (cuuint64_t)M.G.s[0] * esz};
@@ -929,7 +1009,7 @@ int setup_fused(Run &R)
     EncodeTiledFn encode = get_encode();
     if (!encode) return fail("cuTensorMapEncodeTiled not available from the driver");
     const int m = M.m;
-    const int VZ = m == 1 ? FusedCfg<1>::VZ : FusedCfg<2>::VZ, VY = OPESCI_FUSED_EY + 2 * m;
+    const int VZ = m == 1 ? FusedCfg<1>::VZ : FusedCfg<2>::VZ, VY = m == 1 ? FusedCfg<1>::VY : FusedCfg<2>::VY;
     for (int f = 0; f < 3; ++f) {
         cuuint64_t gdim[3] = {(cuuint64_t)p.dim[2], (cuuint64_t)p.dim[1], (cuuint64_t)M.G.dim[0] * p.nlevels};
         cuuint64_t gstride[2] = {(cuuint64_t)M.G.s[1] * 4, (cuuint64_t)M.G.s[0] * 4};
@@ -951,7 +1031,7 @@ int setup_fused(Run &R)
             // extents stop at dim - m: box elements beyond the last interior row / column are not written
             cuuint64_t gdim[3] = {(cuuint64_t)(p.dim[2] - m), (cuuint64_t)(p.dim[1] - m), (cuuint64_t)M.G.dim[0] * p.nlevels};
             cuuint64_t gstride[2] = {(cuuint64_t)M.G.s[1] * 4, (cuuint64_t)M.G.s[0] * 4};
-            cuuint32_t box[3] = {(cuuint32_t)OPESCI_FUSED_EZ, (cuuint32_t)(OPESCI_FUSED_EY - 2 * m), 1};
+            cuuint32_t box[3] = {(cuuint32_t)(m == 1 ? FusedCfg<1>::EZ : FusedCfg<2>::EZ), (cuuint32_t)(m == 1 ? FusedCfg<1>::CY : FusedCfg<2>::CY), 1};
             cuuint32_t estr[3] = {1, 1, 1};
             if (encode(&R.smaps.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, R.dev[ring_field[k]], gdim, gstride, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -965,7 +1045,7 @@ int setup_fused(Run &R)
     // x-chunks: enough CTAs to fill the machine in whole waves, few enough to keep the 2m-plane
     // warm-up of every chunk negligible
     const int nsm = sm_count();
-    const int CZ = m == 1 ? FusedCfg<1>::CZ : FusedCfg<2>::CZ, CY = OPESCI_FUSED_EY - 2 * m;
+    const int CZ = m == 1 ? FusedCfg<1>::CZ : FusedCfg<2>::CZ, CY = m == 1 ? FusedCfg<1>::CY : FusedCfg<2>::CY;
     // z strip: when the last tile row would hold only a few columns, leave them to the per-point kernel
     R.zstrip = 0;
 #ifndef OPESCI_ZSTRIP_MAX
@@ -974,7 +1054,7 @@ int setup_fused(Run &R)
     const int ZS = m == 1 ? FusedCfg<1>::ZS : FusedCfg<2>::ZS;
     {
         const int nzint = p.dim[2] - 2 * m + ZS, rem = nzint % CZ;   // tile bx stores z in [bx*CZ + m - ZS, +CZ)
-        if (rem > 0 && rem <= OPESCI_ZSTRIP_MAX && nzint / CZ >= 2 && !(p.flags & OPESCI_OVERLAP)) R.zstrip = m - ZS + (nzint / CZ) * CZ;
+        if (rem > 0 && rem <= OPESCI_ZSTRIP_MAX && nzint / CZ >= 2) R.zstrip = m - ZS + (nzint / CZ) * CZ;
     }
     const int nztiles = ((R.zstrip > 0 ? R.zstrip : p.dim[2] - m) - m + ZS + CZ - 1) / CZ;
     const long long tiles = (long long)nztiles * ((p.dim[1] - 2 * m + CY - 1) / CY);
@@ -1013,36 +1093,6 @@ int setup_fused(Run &R)
             if (!M.slab.hi_face) { R.xs[c + 1] = M.G.dim[0] - m; ++c; }
             R.nchunks = c;
         }
-    }
-    // (opt-in, OPESCI_OVERLAP: measured no gain on B200 -- a resident fused CTA pins the SM's L1/shared split at
-    // 228 KB shared, and the ghost kernels either cannot co-reside (default carve-out) or lose the L1 they live on)
-    // Overlap of the previous step's ghost loops with this step's fused kernel: tiles whose whole
-    // footprint (reads: core +- 2m in y,z and planes xa-2m .. xb+2m-1; writes: core) stays inside
-    // [2m+1, dim-2m-1)^3 touch no cell those loops read or write.  More x-chunks make more tiles
-    // independent (the two end chunks always depend on the x faces).
-    R.overlap = false;
-    if (M.slab.nranks == 1 && (p.flags & OPESCI_OVERLAP) && nx >= 6 * 48) {
-        const int nc = nx >= 8 * 96 ? 8 : 6;
-        R.nchunks = nc;
-        uniform(m, M.G.dim[0] - m, nc, 0);
-        const int EY = OPESCI_FUSED_EY, EZ = OPESCI_FUSED_EZ;
-        const int dims[3] = {M.G.dim[1], M.G.dim[2], M.G.dim[0]};
-        const int ntile[3] = {(p.dim[1] - 2 * m + CY - 1) / CY, nztiles, nc};
-        for (int a = 0; a < 3; ++a) {
-            int lo = ntile[a], hi = 0;
-            for (int k = 0; k < ntile[a]; ++k) {
-                int rlo, rhi;   // read footprint [rlo, rhi)
-                if (a == 0) { rlo = k * CY - m; rhi = k * CY + EY + m; }
-                else if (a == 1) { rlo = k * CZ - m - ZS; rhi = k * CZ + EZ + m - ZS; }
-                else {
-                    const int xa = R.xs[k], xb = R.xs[k + 1];
-                    rlo = xa - 2 * m; rhi = xb + 2 * m + 1;
-                }
-                if (rlo >= 2 * m + 1 && rhi <= dims[a] - 2 * m - 1) { if (k < lo) lo = k; if (k + 1 > hi) hi = k + 1; }
-            }
-            R.box_lo[a] = lo; R.box_hi[a] = hi;
-        }
-        R.overlap = R.box_hi[0] > R.box_lo[0] && R.box_hi[1] > R.box_lo[1] && R.box_hi[2] > R.box_lo[2];
     }
 #if OPESCI_PACE > 0
     if (!R.d_pace) CUDA_OK(cudaMalloc(&R.d_pace, (size_t)tiles * OPESCI_MAX_CHUNKS * sizeof(int)));
@@ -1084,6 +1134,33 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
         cudaStream_t st = xs_;
         const OpesciSlab &sl = M.slab;
         const size_t plane = (size_t)M.G.s[0], nel = (size_t)sl.halo * plane;
+        if (tl_loop) {
+            // loopback transport: same planes, same direction, same stream position as the NCCL group below
+            Loopback &L = *tl_loop;
+            const int r = sl.rank;
+            CUDA_OK(cudaEventRecord(L.done[r], st));                 // my planes of this level are final
+            if (L.barrier.wait()) return fail("loopback slabs: a peer rank failed");
+            for (int side = 0; side < 2; ++side) {
+                const int nb = side == 0 ? r - 1 : r + 1;
+                if (nb < 0 || nb >= L.nranks) continue;
+                const Run &N = *L.runs[nb];
+                const OpesciSlab &ns = N.M.slab;
+                CUDA_OK(cudaStreamWaitEvent(st, L.done[nb], 0));
+                for (int f = 0; f < p.nfields; ++f) {
+                    T *mine = (T *)R.dev[f] + (size_t)level * M.G.level;
+                    const T *theirs = (const T *)N.dev[f] + (size_t)level * N.M.G.level;
+                    // low halo [X0-halo, X0) = the neighbour's last owned planes; high halo [X1, X1+halo) = its first ones
+                    const size_t dst = side == 0 ? 0 : (size_t)(sl.X1 - sl.L0);
+                    const size_t src = side == 0 ? (size_t)(sl.X0 - sl.halo - ns.L0) : (size_t)(sl.X1 - ns.L0);
+                    CUDA_OK(cudaMemcpyAsync(mine + dst * plane, theirs + src * plane, nel * sizeof(T), cudaMemcpyDeviceToDevice, st));
+                }
+            }
+            CUDA_OK(cudaEventRecord(L.xdone[r], st));                // I have read my neighbours' planes
+            if (L.barrier.wait()) return fail("loopback slabs: a peer rank failed");
+            for (int nb = r - 1; nb <= r + 1; nb += 2)
+                if (nb >= 0 && nb < L.nranks) CUDA_OK(cudaStreamWaitEvent(st, L.xdone[nb], 0));
+            return 0;
+        }
         NCCL_OK(g_nccl.GroupStart());
         for (int f = 0; f < p.nfields; ++f) {
             T *base = (T *)R.dev[f] + (size_t)level * M.G.level;
@@ -1116,84 +1193,38 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
         if (e) return fail("%s", e);
     }
 #define SNAP_OK(call) do { const char *e_ = (call); if (e_) return fail("%s", e_); } while (0)
-    cudaEvent_t e0, e1;
+    // every handle of the time loop lives in one holder whose destructor runs on each early `return` of the error
+    // macros too: a capture left open is ended, graphs / events / the second stream are destroyed
+    struct LoopHandles {
+        cudaStream_t cap = nullptr;     // stream with a capture in progress
+        cudaEvent_t e0 = nullptr, e1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t gexec = nullptr;
+        cudaStream_t st2 = nullptr;
+        ~LoopHandles()
+        {
+            if (cap) { cudaGraph_t g = nullptr; cudaStreamEndCapture(cap, &g); if (g) cudaGraphDestroy(g); cudaGetLastError(); }
+            if (gexec) cudaGraphExecDestroy(gexec);
+            if (graph) cudaGraphDestroy(graph);
+            if (e0) cudaEventDestroy(e0);
+            if (e1) cudaEventDestroy(e1);
+            if (ev_fork) cudaEventDestroy(ev_fork);
+            if (ev_join) cudaEventDestroy(ev_join);
+            if (st2) cudaStreamDestroy(st2);
+        }
+    } H;
+    cudaEvent_t &e0 = H.e0, &e1 = H.e1;
     CUDA_OK(cudaEventCreate(&e0));
     CUDA_OK(cudaEventCreate(&e1));
     const int nsteps = p.ntsteps;
     int warm = p.warmup_steps > 0 ? p.warmup_steps : 0;   // the first `warmup_steps` steps run untimed (bench contract)
     if (warm > nsteps) warm = nsteps;
     long long per_period = 0;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t gexec = nullptr;
-    cudaStream_t st2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    const bool pipelined = staggered && R.fused && R.overlap && !slabs && !snap.armed;
-    if (pipelined) {
-        // ---- software-pipelined stepping: the ghost loops + shell update of step n-1 (latency-bound, they
-        // leave most of the machine idle) run on a second stream concurrently with the tiles of step n that
-        // cannot see them; the remaining tiles of step n follow.  Same kernels, same per-cell order.
-        CUDA_OK(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
-        CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-        CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-        Stepper SB(R, st2);
-        auto ghost = [&](Stepper &X, int ti) {   // everything of step ti after the fused kernel
-            const int t0 = ti % 2, t1 = (t0 + 1) % 2;
-            X.template stress_bc<T>(t0, t1, false);
-            X.template velocity_shell<SO, T, ARITH>(t0, t1);
-            X.template velocity_bc<T>(t1);
-            X.template point_hooks<T>(t1);
-        };
-        auto step = [&](int ti, bool has_prev) -> int {
-            const int t0 = ti % 2, t1 = (t0 + 1) % 2;
-            if (has_prev) {
-                CUDA_OK(cudaEventRecord(ev_fork, st));
-                CUDA_OK(cudaStreamWaitEvent(st2, ev_fork, 0));
-                ghost(SB, ti - 1);
-                CUDA_OK(cudaEventRecord(ev_join, st2));
-            }
-            S.template fused<SO, T, ARITH>(t0, t1, 1);        // tiles independent of the ghost loops
-            if (has_prev) CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));
-            S.template fused<SO, T, ARITH>(t0, t1, 2);        // the remaining tiles
-            return 0;
-        };
-        const bool use_graph2 = !(p.flags & OPESCI_NO_CUDA_GRAPH) && nsteps >= 6;
-        if (use_graph2) {
-            // steady state of two consecutive steps (odd ti, then even ti), captured across both streams
-            CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const long long before = S.launches + SB.launches;
-            if (step(1, true) || step(2, true)) return 1;
-            per_period = S.launches + SB.launches - before;
-            CUDA_OK(cudaStreamEndCapture(st, &graph));
-            CUDA_OK(cudaGraphInstantiate(&gexec, graph, 0));
-            S.launches = SB.launches = 0;
-        }
-        long long graph_launches = 0;
-        auto run_range = [&](int a, int b) -> int {   // steps a .. b-1, pipeline drained at the end
-            int ti = a;
-            while (ti < b) {
-                if (gexec && ti > a && (ti & 1) && ti + 2 <= b) {
-                    CUDA_OK(cudaGraphLaunch(gexec, st));
-                    graph_launches += per_period;
-                    ti += 2;
-                } else {
-                    if (step(ti, ti > a)) return 1;
-                    ++ti;
-                }
-            }
-            if (b > a) ghost(S, b - 1);
-            return 0;
-        };
-        if (warm > 0 && run_range(0, warm)) return 1;
-        S.launches = SB.launches = 0;
-        graph_launches = 0;
-        CUDA_OK(cudaEventRecord(e0, st));
-        if (run_range(warm, nsteps)) return 1;
-        CUDA_OK(cudaEventRecord(e1, st));
-        CUDA_OK(cudaStreamSynchronize(st));
-        CUDA_OK(cudaStreamSynchronize(st2));
-        S.launches += SB.launches + graph_launches;
-        if (SB.err != cudaSuccess && S.err == cudaSuccess) S.err = SB.err;
-    } else if (slabs && staggered && R.fused && R.mid1 > R.mid0) {
+    cudaGraph_t &graph = H.graph;
+    cudaGraphExec_t &gexec = H.gexec;
+    cudaStream_t &st2 = H.st2;
+    cudaEvent_t &ev_fork = H.ev_fork, &ev_join = H.ev_join;
+    if (slabs && staggered && R.fused && R.mid1 > R.mid0) {
         // ---- slabs, fused kernel: the halo exchange of step n (NCCL, own high-priority stream) runs while the middle
         // x-chunks of step n+1 -- which read no halo plane -- are computed; the thin end chunks, the ghost loops and
         // the shell follow once the exchange has landed.  Same kernels, same per-cell order as the serial schedule.
@@ -1206,10 +1237,10 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
         auto step = [&](int ti) -> int {
             const int t0 = ti % 2, t1 = (t0 + 1) % 2;
             SNAP_OK(snap.before_step(st, ti));
-            S.template fused<SO, T, ARITH>(t0, t1, 0, R.mid0, R.mid1 - R.mid0);
+            S.template fused<SO, T, ARITH>(t0, t1, R.mid0, R.mid1 - R.mid0);
             if (pending) { CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0)); pending = false; }
-            S.template fused<SO, T, ARITH>(t0, t1, 0, 0, R.mid0);
-            S.template fused<SO, T, ARITH>(t0, t1, 0, R.mid1, R.nchunks - R.mid1);
+            S.template fused<SO, T, ARITH>(t0, t1, 0, R.mid0);
+            S.template fused<SO, T, ARITH>(t0, t1, R.mid1, R.nchunks - R.mid1);
             S.template stress_bc<T>(t0, t1, false);
             S.template velocity_shell<SO, T, ARITH>(t0, t1);
             S.template velocity_bc<T>(t1);
@@ -1242,12 +1273,14 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     if (use_graph) {
         // one period of steps (time-level indices repeat with it) captured once, replayed
         CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        H.cap = st;
         const long long before = S.launches;
         for (int ti = 0; ti < period; ++ti) {
             if (staggered) S.template staggered_step<SO, T, ARITH>(ti);
             else S.template acoustic_step<SO, T, ARITH>(ti);
         }
         per_period = S.launches - before;
+        H.cap = nullptr;
         CUDA_OK(cudaStreamEndCapture(st, &graph));
         CUDA_OK(cudaGraphInstantiate(&gexec, graph, 0));
         S.launches = before;
@@ -1288,14 +1321,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
     *loop_seconds = ms * 1e-3;
     g_launches = S.launches;
-    if (gexec) cudaGraphExecDestroy(gexec);
-    if (graph) cudaGraphDestroy(graph);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    if (ev_fork) cudaEventDestroy(ev_fork);
-    if (ev_join) cudaEventDestroy(ev_join);
-    if (st2) cudaStreamDestroy(st2);
-    return 0;
+    return 0;   // ~LoopHandles releases the graph, events and the second stream
 }
 
 template <typename T, int ARITH> int dispatch_so(Run &R, cudaStream_t st, double *secs)
@@ -1532,6 +1558,7 @@ template <typename T> int l2_sums(Run &R, const void *const *level_base_dev, dou
         l2_partial<T><<<grids[f], blk, 0, st>>>((const T *)level_base_dev[f], M.G, ranges[f], R.d_prog + 2 * f + 1, d_partial);
         l2_final<<<1, 1024, 0, st>>>(d_partial, nb, d_out + f);
     }
+    if (M.slab.nranks > 1 && !g_nccl.comm) return fail("L2 norms of a slab need the NCCL communicator (loopback slabs: compare the fields instead)");
     if (M.slab.nranks > 1) {
         // sum of the per-slab partial sums (ncclAllReduce of 9 doubles)
         NCCL_OK(g_nccl.AllReduce(d_out, d_out, OPESCI_MAX_FIELDS, ncclFloat64, ncclSum, g_nccl.comm, st));
@@ -1543,8 +1570,63 @@ template <typename T> int l2_sums(Run &R, const void *const *level_base_dev, dou
     return 0;
 }
 
+// OPESCI_L2_REFERENCE: accumulators of the reference's serial real_t sums (kernels.cuh: l2_terms / l2_serial).
+// acc_out[f] holds the final accumulator of field f converted to double (exact).
+template <typename T> int l2_reference(Run &R, const void *const *level_base_dev, double *acc_out)
+{
+    const Model &M = R.M;
+    if (M.slab.nranks > 1) return fail("OPESCI_L2_REFERENCE: the serial reference-order sum needs the whole domain on one rank");
+    cudaStream_t st = 0;
+    const int nf = M.p.nfields;
+    Range3 full[OPESCI_MAX_FIELDS];
+    size_t plane_cells = 1;
+    int xlo = 1 << 30, xhi = 0;
+    for (int f = 0; f < nf; ++f) {
+        const OpesciFieldSpec &fs = M.p.fields[f];
+        for (int d = 0; d < 3; ++d) { full[f].lo[d] = fs.l2_lo[d]; full[f].hi[d] = fs.l2_hi[d]; }
+        const size_t ny = full[f].hi[1] > full[f].lo[1] ? full[f].hi[1] - full[f].lo[1] : 0;
+        const size_t nz = full[f].hi[2] > full[f].lo[2] ? full[f].hi[2] - full[f].lo[2] : 0;
+        if (ny * nz > plane_cells) plane_cells = ny * nz;
+        if (full[f].lo[0] < xlo) xlo = full[f].lo[0];
+        if (full[f].hi[0] > xhi) xhi = full[f].hi[0];
+    }
+    // chunks of whole x planes, about 4 M cells per field and chunk
+    int px = (int)((size_t)(4u << 20) / plane_cells);
+    if (px < 1) px = 1;
+    const size_t stride = (size_t)px * plane_cells;
+    double *d_terms = nullptr;
+    T *d_acc = nullptr;
+    CUDA_OK(cudaMalloc(&d_terms, (size_t)nf * stride * sizeof(double)));
+    if (cudaMalloc(&d_acc, OPESCI_MAX_FIELDS * sizeof(T)) != cudaSuccess) { cudaFree(d_terms); return fail("OPESCI_L2_REFERENCE: out of device memory"); }
+    cudaMemsetAsync(d_acc, 0, OPESCI_MAX_FIELDS * sizeof(T), st);
+    dim3 blk(64, 4);
+    for (int x0 = xlo; x0 < xhi; x0 += px) {
+        L2SerialArgs N;
+        for (int f = 0; f < OPESCI_MAX_FIELDS; ++f) N.count[f] = 0;
+        for (int f = 0; f < nf; ++f) {
+            Range3 rg = full[f];
+            rg.lo[0] = rg.lo[0] > x0 ? rg.lo[0] : x0;
+            rg.hi[0] = rg.hi[0] < x0 + px ? rg.hi[0] : x0 + px;
+            const int nz = rg.hi[2] - rg.lo[2], ny = rg.hi[1] - rg.lo[1], nx = rg.hi[0] - rg.lo[0];
+            if (nz <= 0 || ny <= 0 || nx <= 0) continue;
+            N.count[f] = (long long)nx * ny * nz;
+            dim3 grid((nz + blk.x - 1) / blk.x, (ny + blk.y - 1) / blk.y, nx);
+            l2_terms<T><<<grid, blk, 0, st>>>((const T *)level_base_dev[f], M.G, rg, R.d_prog + 2 * f + 1, d_terms + (size_t)f * stride);
+        }
+        l2_serial<T><<<nf, 256, 0, st>>>(d_terms, stride, N, d_acc);
+    }
+    T h_acc[OPESCI_MAX_FIELDS];
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(h_acc, d_acc, sizeof h_acc, cudaMemcpyDeviceToHost);
+    cudaFree(d_terms);
+    cudaFree(d_acc);
+    if (e != cudaSuccess) return fail("OPESCI_L2_REFERENCE: %s", cudaGetErrorString(e));
+    for (int f = 0; f < nf; ++f) acc_out[f] = (double)h_acc[f];
+    return 0;
+}
+
 // L2 sums of the level `ntsteps % 2` (the reference's `ti`, also for tp == 3: regulargrid.py:664)
-int convergence_sums(OpesciGrid *grid, double *sums, Model **model_out)
+int convergence_sums(OpesciGrid *grid, double *sums, Model **model_out, bool reference_order = false)
 {
     Run *R = find_run(grid);
     Run *tmp = nullptr;
@@ -1582,11 +1664,32 @@ int convergence_sums(OpesciGrid *grid, double *sums, Model **model_out)
             base[f] = d;
         }
     }
-    int rc = M.p.is_double ? l2_sums<double>(*R, base, sums) : l2_sums<float>(*R, base, sums);
+    int rc;
+    if (reference_order) rc = M.p.is_double ? l2_reference<double>(*R, base, sums) : l2_reference<float>(*R, base, sums);
+    else rc = M.p.is_double ? l2_sums<double>(*R, base, sums) : l2_sums<float>(*R, base, sums);
     for (void *u : uploaded) cudaFree(u);
     if (model_out) *model_out = &g_model;
     if (tmp) release(tmp);
     return rc;
+}
+
+// x-slab of rank `rank` of `nranks` and the geometry of the planes it stores (include/opesci_slab.h)
+int apply_slab(Model &M, int rank, int nranks)
+{
+    const OpesciB200Params &p = M.p;
+    const int need = opesci_slab_need(p.kind == OPESCI_KIND_REGULAR_ACOUSTIC, p.so);
+    if (opesci_slab_make(&M.slab, rank, nranks, p.dim[0], M.m, OPESCI_SLAB_HALO, need)) return 1;
+    for (int d = 0; d < 3; ++d) M.G.dim[d] = p.dim[d];
+    M.G.dim[0] = M.slab.L1 - M.slab.L0;   // local planes; p.dim[0] stays the global dim1
+    M.G.m = M.m;
+    // device rows are padded to a multiple of 32 elements (TMA needs 16-B row strides; 128-B rows
+    // keep tiles sector-aligned); the host arrays keep the reference's dense layout
+    const long long pitch = ((long long)p.dim[2] + 31) / 32 * 32;
+    M.G.s[0] = (long long)p.dim[1] * pitch;
+    M.G.s[1] = pitch;
+    M.G.s[2] = 1;
+    M.G.level = (long long)M.G.dim[0] * p.dim[1] * pitch;
+    return 0;
 }
 
 }  // namespace
@@ -1609,21 +1712,10 @@ int opesci_b200_configure(const OpesciB200Params *params)
     M.p = *params;
     M.m = params->so / 2;
     const int nranks = params->slab_nranks > 1 ? params->slab_nranks : 1;
-    const int need = opesci_slab_need(params->kind == OPESCI_KIND_REGULAR_ACOUSTIC, params->so);   // include/opesci_slab.h
-    if (opesci_slab_make(&M.slab, nranks > 1 ? params->slab_rank : 0, nranks, params->dim[0], M.m, OPESCI_SLAB_HALO, need))
+    if (apply_slab(M, nranks > 1 ? params->slab_rank : 0, nranks))
         return fail("opesci_b200_configure: slabs thinner than the halo: use fewer ranks");
     if (nranks > 1 && (!g_nccl.comm || g_nccl.nranks != nranks || g_nccl.rank != params->slab_rank))
         return fail("opesci_b200_configure: slab_nranks > 1 needs opesci_b200_comm_init with the same rank / size first");
-    for (int d = 0; d < 3; ++d) M.G.dim[d] = params->dim[d];
-    M.G.dim[0] = M.slab.L1 - M.slab.L0;   // local planes; p.dim[0] stays the global dim1
-    M.G.m = M.m;
-    // device rows are padded to a multiple of 32 elements (TMA needs 16-B row strides; 128-B rows
-    // keep tiles sector-aligned); the host arrays keep the reference's dense layout
-    const long long pitch = ((long long)params->dim[2] + 31) / 32 * 32;
-    M.G.s[0] = (long long)params->dim[1] * pitch;
-    M.G.s[1] = pitch;
-    M.G.s[2] = 1;
-    M.G.level = (long long)M.G.dim[0] * params->dim[1] * pitch;
     memcpy(M.sc.sn, params->c_stress_normal, sizeof M.sc.sn);
     memcpy(M.sc.ss, params->c_stress_shear, sizeof M.sc.ss);
     memcpy(M.sc.v, params->c_velocity, sizeof M.sc.v);
@@ -1688,15 +1780,15 @@ int opesci_b200_configure(const OpesciB200Params *params)
     return 0;
 }
 
-int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
+static int execute_model(const Model &model, OpesciGrid *grid, OpesciProfiling *profiling)
 {
-    if (!g_model.configured) return fail("opesci_execute: opesci_b200_configure was not called");
     const auto wall0 = std::chrono::steady_clock::now();
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("opesci_execute: no CUDA device (this library has no CPU fallback)");
     Run *R = new Run();
-    R->M = g_model;
+    R->M = model;
+    if (tl_loop) tl_loop->runs[model.slab.rank] = R;   // peers read it after the first barrier of an exchange
     const OpesciB200Params &p = R->M.p;
     const size_t esz = p.is_double ? 8 : 4;
     R->bytes_per_field = (size_t)R->M.G.level * p.nlevels * esz;
@@ -1717,7 +1809,7 @@ int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
     if (setup_hooks(*R)) return bail(1);
     double secs = 0.0;
     if (dispatch(*R, st, &secs)) return bail(1);
-    g_loop_seconds = secs;
+    if (!tl_loop || model.slab.rank == 0) g_loop_seconds = secs;
     if (p.n_receivers > 0 && p.receiver_out && p.ntsteps > 0 &&
         cudaMemcpy(p.receiver_out, R->d_recv_out, (size_t)p.ntsteps * 4 * p.n_receivers * esz, cudaMemcpyDeviceToHost) != cudaSuccess)
         return bail(fail("opesci_execute: copying the receiver data back failed"));
@@ -1755,6 +1847,65 @@ int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
     return 0;
 }
 
+int opesci_execute(OpesciGrid *grid, OpesciProfiling *profiling)
+{
+    if (!g_model.configured) return fail("opesci_execute: opesci_b200_configure was not called");
+    return execute_model(g_model, grid, profiling);
+}
+
+int opesci_b200_execute_loopback(int nranks, OpesciGrid *grids)
+{
+    if (!g_model.configured) return fail("opesci_b200_execute_loopback: opesci_b200_configure was not called");
+    if (g_model.slab.nranks > 1) return fail("opesci_b200_execute_loopback: configure the whole domain (slab_nranks <= 1)");
+    if (nranks < 2 || !grids) return fail("opesci_b200_execute_loopback: need nranks >= 2 and one OpesciGrid per rank");
+    if (g_model.p.n_receivers > 0 || g_model.p.src_nt > 0) return fail("opesci_b200_execute_loopback: point source / receivers are per process");
+    if (opesci_io::output_cfg().armed) return fail("opesci_b200_execute_loopback: per-step output is per process");
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail("opesci_b200_execute_loopback: no CUDA device");
+    Loopback L;
+    L.nranks = nranks;
+    L.runs.assign(nranks, nullptr);
+    L.done.assign(nranks, nullptr);
+    L.xdone.assign(nranks, nullptr);
+    L.barrier.n = nranks;
+    std::vector<Model> models(nranks, g_model);
+    for (int r = 0; r < nranks; ++r) {
+        models[r].p.slab_rank = r;
+        models[r].p.slab_nranks = nranks;
+        if (apply_slab(models[r], r, nranks)) return fail("opesci_b200_execute_loopback: slabs thinner than the halo: use fewer ranks");
+        if (cudaEventCreateWithFlags(&L.done[r], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&L.xdone[r], cudaEventDisableTiming) != cudaSuccess)
+            return fail("opesci_b200_execute_loopback: cudaEventCreate failed");
+    }
+    std::vector<int> rc(nranks, 0);
+    std::vector<std::string> errs(nranks);
+    std::mutex err_mu;
+    std::vector<std::thread> threads;
+    for (int r = 0; r < nranks; ++r)
+        threads.emplace_back([&, r] {
+            cudaSetDevice(dev);
+            tl_loop = &L;
+            rc[r] = execute_model(models[r], &grids[r], nullptr);
+            if (rc[r]) {
+                { std::lock_guard<std::mutex> lk(err_mu); errs[r] = g_err; }
+                L.barrier.abort();     // peers waiting in an exchange give up instead of waiting for ever
+            }
+            tl_loop = nullptr;
+        });
+    for (auto &t : threads) t.join();
+    cudaDeviceSynchronize();
+    for (int r = 0; r < nranks; ++r) { cudaEventDestroy(L.done[r]); cudaEventDestroy(L.xdone[r]); }
+    int bad = -1;
+    for (int r = 0; r < nranks; ++r)
+        if (rc[r] && (bad < 0 || errs[r].find("peer rank failed") == std::string::npos)) bad = r;
+    if (bad >= 0) {
+        for (int r = 0; r < nranks; ++r)
+            if (!rc[r]) opesci_free(&grids[r]);
+        return fail("loopback rank failed: %s", errs[bad].c_str());
+    }
+    return 0;
+}
+
 int opesci_b200_convergence_f64(OpesciGrid *grid, double *out_l2)
 {
     double sums[OPESCI_MAX_FIELDS];
@@ -1767,15 +1918,21 @@ int opesci_b200_convergence_f64(OpesciGrid *grid, double *out_l2)
 
 int opesci_convergence(OpesciGrid *grid, OpesciConvergence *conv)
 {
-    // staggeredgrid.py:892-945: conv->F_l2 = pow(F_l2 * volume_literal, 0.5) in real_t.  The
-    // sum is accumulated in double by a deterministic tree (the reference accumulates serially
-    // in real_t, which loses digits on large grids: SURVEY.md 7 "hard parts").
+    // staggeredgrid.py:892-945: conv->F_l2 = pow(F_l2 * volume_literal, 0.5) in real_t.
+    // Default: the sum is accumulated in double by a deterministic tree (the reference accumulates serially in real_t,
+    // which loses digits on large grids: SURVEY.md 7 "hard parts").  With OPESCI_L2_REFERENCE the reference's own serial
+    // real_t accumulation is performed instead, so the printed digits are the reference's.
     double sums[OPESCI_MAX_FIELDS];
     Run *R = find_run(grid);
     const Model &M = R ? R->M : g_model;
-    if (convergence_sums(grid, sums, nullptr)) return 1;
+    const bool ref_order = (M.p.flags & OPESCI_L2_REFERENCE) != 0;
+    if (convergence_sums(grid, sums, nullptr, ref_order)) return 1;
     for (int f = 0; f < M.p.nfields; ++f) {
-        if (M.p.is_double) conv->f64[f] = sqrt(sums[f] * (double)(float)M.p.volume_literal);
+        if (ref_order) {
+            // `F_l2 = pow(F_l2 * volume, 0.5)` as emitted: real_t product, libm pow in double, result stored as real_t
+            if (M.p.is_double) conv->f64[f] = pow(sums[f] * (double)(float)M.p.volume_literal, 0.5);
+            else conv->f32[f] = (float)pow((double)((float)sums[f] * (float)M.p.volume_literal), 0.5);
+        } else if (M.p.is_double) conv->f64[f] = sqrt(sums[f] * (double)(float)M.p.volume_literal);
         else conv->f32[f] = (float)sqrt((double)((float)sums[f] * (float)M.p.volume_literal));
     }
     return 0;
@@ -1851,11 +2008,19 @@ int opesci_b200_comm_finalize(void)
 int opesci_b200_reserve_host(size_t bytes_per_array, int count)
 {
     std::vector<void *> got;
+    g_pool_reserving = true;     // blocks created from here on survive opesci_free (single-threaded caller, like the whole ABI)
     for (int i = 0; i < count; ++i) {
         bool pinned = false;
         void *p = pool_alloc(bytes_per_array, &pinned);
-        if (!p) { for (void *q : got) pool_release(q); return fail("opesci_b200_reserve_host: allocation failed"); }
+        if (!p) { g_pool_reserving = false; for (void *q : got) pool_release(q); return fail("opesci_b200_reserve_host: allocation failed"); }
         got.push_back(p);
+    }
+    g_pool_reserving = false;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (auto &b : g_pool)
+            for (void *q : got)
+                if (b.ptr == q) b.reserved = true;    // an idle on-demand block that was reused counts as reserved too
     }
     for (void *q : got) pool_release(q);
     return 0;

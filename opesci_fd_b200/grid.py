@@ -8,6 +8,7 @@ library through `opesci_b200_configure`; `opesci_execute` / `opesci_convergence`
 called exactly like the reference calls its generated functions (grid.py:118-122, 150-156).
 """
 import ctypes
+import os
 import json
 from ctypes import byref
 from os import environ
@@ -148,6 +149,9 @@ class Grid(object):
             self.free()
         self._params, self._params_keepalive = self.build_params()
         self._params.flags = int(self.b200_flags)
+        if os.environ.get("OPESCI_L2_REFERENCE", "0") not in ("", "0"):
+            # convergence() prints the reference's own digits (serial real_t accumulation, staggeredgrid.py:916,935)
+            self._params.flags |= abi.L2_REFERENCE
         lib = self._library
         if lib.opesci_b200_configure(byref(self._params)) != 0:
             raise RuntimeError("opesci_b200_configure: %s" % lib.opesci_b200_last_error().decode())
@@ -203,9 +207,18 @@ You need to you run grid.execute() first!""")
         self._arg_grid = None
 
     def field_array(self, k):
-        """numpy view [nlevels][dim1][dim2][dim3] of host field k (HOST_MIRROR_FULL only)."""
+        """numpy view [nlevels][dim1][dim2][dim3] of host field k (HOST_MIRROR_FULL only).
+
+        The view aliases the library's result array: it is valid until free() / the next run() of this grid
+        (opesci_free hands the block back to the library's host pool).  Copy it to keep it longer.
+        """
         import numpy as np
+        if self._arg_grid is None:
+            raise RuntimeError("field_array: no results (run() first; free() releases them)")
         p = self._params
+        if (int(p.flags) & abi.HOST_MIRROR_MASK) != abi.HOST_MIRROR_FULL:
+            raise RuntimeError("field_array: the fields were left on the device (HOST_MIRROR_NONE); "
+                               "grid->field[] are device pointers")
         n = p.nlevels * p.dim[0] * p.dim[1] * p.dim[2]
         ctype = ctypes.c_double if p.is_double else ctypes.c_float
         buf = ctypes.cast(self._arg_grid.field[k], ctypes.POINTER(ctype * n)).contents

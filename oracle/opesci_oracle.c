@@ -5,7 +5,7 @@
  * executed only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.  It is
  * never on the product path (the product is opesci_fd_b200/csrc, CUDA only).
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this restatement
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks this restatement
  * BIT-FOR-BIT against the reference's own generated OpenMP C++ (oracle/_ref, built by
  * oracle/refgen/make_ref.py from /root/reference) for so = 2..12, fp32 and fp64, staggered
  * and regular grids, and against the committed golden fixtures in tests/golden/.
@@ -673,6 +673,7 @@ int opesci_b200_slab_range(int rank, int nranks, int gdim1, int so, int *L0, int
     if (L1) *L1 = sl.L1;
     return 0;
 }
+int opesci_b200_execute_loopback(int nranks, OpesciGrid *grids) { (void)nranks; (void)grids; return fail("opesci_b200_execute_loopback: CUDA library only"); }
 int opesci_b200_reserve_host(size_t bytes_per_array, int count) { (void)bytes_per_array; (void)count; return 0; }
 int opesci_b200_release_host(void) { return 0; }
 

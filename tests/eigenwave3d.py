@@ -203,7 +203,12 @@ converge:  Convergence test of the (2,4) scheme, which is 2nd order
     p.add_argument('--double', action='store_true', default=False, help='use double precision fields')
     p.add_argument('--synthetic', action='store_true', default=False,
                    help='read mode: use the synthetic random medium instead of the data files')
+    p.add_argument('--reference-l2', dest='reference_l2', action='store_true', default=False,
+                   help='accumulate the L2 norms like the generated C++ does (serially, in real_t, in loop order): '
+                        'prints the reference\'s own digits; slower (a serial chain)')
     args = p.parse_args()
+    if args.reference_l2:
+        os.environ['OPESCI_L2_REFERENCE'] = '1'
     print("Eigenwave3D example (mode=%s)" % args.mode)
 
     if args.mode == 'default':

@@ -91,7 +91,12 @@ def main():
     p.add_argument('--pluto', action='store_true', default=False)
     p.add_argument('--fission', action='store_true', default=False)
     p.add_argument('--double', action='store_true', default=False)
+    p.add_argument('--reference-l2', dest='reference_l2', action='store_true', default=False,
+                   help='accumulate the L2 norms like the generated C++ does (serially, in real_t, in loop order): '
+                        'prints the reference\'s own digits; slower (a serial chain)')
     args = p.parse_args()
+    if args.reference_l2:
+        os.environ['OPESCI_L2_REFERENCE'] = '1'
     print("Simple wave 3D example ")
     default(compiler=args.compiler, execute=args.execute, nthreads=args.nthreads,
             accuracy_order=[2, args.so, args.so, args.so], profiling=args.profiling, double=args.double)
