@@ -32,6 +32,7 @@ FORCE_UNFUSED = 1 << 9
 OVERLAP = 1 << 10
 FORCE_TILED = 1 << 11
 L2_REFERENCE = 1 << 12
+NO_ZFOLD = 1 << 13
 
 FS_NONE, FS_LEVANDER, FS_ROBERTSSON = 0, 1, 2
 

@@ -182,6 +182,22 @@ struct FusedArgs {
     int chunk0;
     int *pace;        // OPESCI_PACE: progress of every tile (plane index; -1 not started; INT_MAX done), else null
     int cluster_sync; // launched as clusters of OPESCI_CLUSTER_Z z-adjacent CTAs (A/B experiment)
+    // tile column of a CTA: blockIdx.x + bx0 (interior launch) or bxs[blockIdx.x] (z-edge launch, ZF kernels)
+    int bx0;
+    int bxs[2];
+    // ---- z-fold (ZF kernels): the z-face stress ghost loops and the z slabs of the velocity shell are done in the
+    // z-edge tiles, for the cells whose operands only z-face loops touch: planes [zf_xlo, zf_xhi), rows [M+1, dim2-M-1)
+    int zf_side[2];   // this launch handles the low / high z face ...
+    int zf_bx[2];     // ... in the tiles of this column
+    int zf_c[2];      // tile column (0..EZ-1) of the face plane b = M / b' = dim3-M-1 inside tile bxs[side]
+    int zf_xlo, zf_xhi;
+    float zf_lev[2][2][2];   // Levander recompute on the z faces: [Txx, Tyy][d/dx U, d/dy V][k] (lev_stress[2][e][f])
+    // The reference mirrors Txx across the x faces (reading plane m+1 / dim1-m-2) and Tyy across the y faces (reading row
+    // m+1 / dim2-m-2) BEFORE the z-face Levander loops rewrite those cells.  On these planes (Txx) / rows (Tyy) the z-edge
+    // tiles therefore keep the recomputed value in registers only (their own velocity update needs it) and store the plain
+    // interior value; the face kernels recompute the cells afterwards, in the reference's order (Stepper::stress_bc).
+    int zf_raw_x[2];         // planes (-1: none -- an artificial slab end has no x face)
+    int zf_raw_y[2];         // rows
 };
 
 // six consecutive floats p[-2..3] as three aligned 8-byte loads (p must be 8-byte aligned)
@@ -260,7 +276,16 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *tmap, const void
                  "r"(c1), "r"(c2)
                  : "memory");
 }
-template <int SO, int ARITH, bool HET = false>
+// ZF = true: the z-edge variant (tile columns 0 and last).  After the interior stress update of a plane it applies,
+// in registers, what the reference's z-face stress loops do to the cells of that plane (opesci/staggeredgrid.py:750-813
+// through opesci/fields.py:313-381, so = 4): Levander recompute of Txx, Tyy on the face plane from level t0, Tzz = 0 on
+// it, antisymmetric mirrors of Tzz, Tyz, Txz into the ghost columns -- in the reference's own operation order -- and
+// stores the ghost columns; the velocity update then also covers the z slabs of the shell [M, 2M+1) / [dim-2M-1, dim-M),
+// whose stress operands are now final.  Restricted to the "pure" zone (planes [zf_xlo, zf_xhi), rows [M+1, dim2-M-1)):
+// there no x-/y-face loop writes any cell these operations read or write, so the result is cell for cell what the
+// separate face kernels produce; the thin remainder next to the x / y faces stays with them (Stepper::stress_bc).
+// A separate instantiation, so the interior tiles keep their register budget.
+template <int SO, int ARITH, bool HET = false, bool ZF = false>
 __global__ void __launch_bounds__(FusedCfg<SO / 2>::THREADS, OPESCI_FUSED_MINB)
 fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
            const __grid_constant__ CUtensorMap tmW, const FusedArgs A
@@ -299,8 +324,13 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 #endif
     const GridGeom &G = A.G;
     const int tid = threadIdx.x;
+    // Programmatic dependent launch: the interior launch that follows the z-edge launch in the stream does not depend on
+    // it (disjoint cells, both read level t0 only) -- let its CTAs start as soon as SMs free up instead of after the last,
+    // partly filled wave of z-edge CTAs.  (The interior kernel waits for the z-edge grid just before it exits, below.)
+    if (ZF) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int bx = ZF ? A.bxs[blockIdx.x] : (int)blockIdx.x + A.bx0;       // tile column
     const int tz = 2 * (tid % (K::EZ / 2)), ty = tid / (K::EZ / 2);          // lane 0 sits at tz, lane 1 at tz+1
-    const int ye = blockIdx.y * K::CY + ty, ze = blockIdx.x * K::CZ + tz - K::ZS;   // global coords of lane 0 (ze < 0: outside)
+    const int ye = blockIdx.y * K::CY + ty, ze = bx * K::CZ + tz - K::ZS;   // global coords of lane 0 (ze < 0: outside)
     const int chunk = blockIdx.z + A.chunk0;
     const int xa = A.xs[chunk];
     const int xb = A.xs[chunk + 1];
@@ -309,7 +339,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     // x loop unrolled RD times every slot index below is a compile-time constant
     const int pbaseU = xs_begin - M, pbaseVW = xs_begin - M + 1;
     const int lastU = xs_end + M - 2, lastVW = xs_end + M - 1;
-    const int c0 = blockIdx.x * K::CZ - K::OFFZ, c1 = blockIdx.y * K::CY - M;   // TMA box origin (may be negative)
+    const int c0 = bx * K::CZ - K::OFFZ, c1 = blockIdx.y * K::CY - M;   // TMA box origin (may be negative)
     const int lvl0 = A.t0 * G.dim[0];
     constexpr uint32_t TILE_BYTES = K::VZ * K::VY * 4;
 
@@ -346,8 +376,12 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
         const bool core = ty >= M && ty < M + K::CY && t >= M && t < M + K::CZ;
         inb[L] = ye < G.dim[1] && z >= 0 && z < G.dim[2];
         st_yz[L] = core && ye >= M && ye < G.dim[1] - M && z >= M && z < G.dim[2] - M;
-        vf_yz[L] = core && ye >= 2 * M + 1 && ye < G.dim[1] - 2 * M - 1 && z >= 2 * M + 1 && z < G.dim[2] - 2 * M - 1;
+        // velocities: deep interior; the z-edge variant also owns the z slabs of the shell (whole interior z range)
+        vf_yz[L] = core && ye >= 2 * M + 1 && ye < G.dim[1] - 2 * M - 1 &&
+                   (ZF ? (z >= M && z < G.dim[2] - M) : (z >= 2 * M + 1 && z < G.dim[2] - 2 * M - 1));
     }
+    // z-fold: rows whose z-face cells see no y-face loop (warp-uniform: a warp is one tile row)
+    const bool zf_row = ZF && ye >= M + 1 && ye < G.dim[1] - M - 1;
     const bool inb2 = inb[0] && inb[1], st2 = st_yz[0] && st_yz[1], vf2 = vf_yz[0] && vf_yz[1];
 #ifndef OPESCI_HALO_SKIP
 #define OPESCI_HALO_SKIP 0   /* measured on B200: 20.85 vs 20.05 ms -- fewer loads and flops, but 113 instead of 106 registers and a warp-level branch per plane */
@@ -357,8 +391,8 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     const bool halo_row = OPESCI_HALO_SKIP && (ty < M || ty >= M + K::CY);
     // CTA-uniform: tiles whose whole 64 x 12 store box lies inside the interior (not the first tile column, whose halo
     // columns are ghost cells; not a ragged last column / row)
-    const bool tma_st = OPESCI_TMA_STORE && !OPESCI_SPLIT_BARRIER && blockIdx.x > 0 &&
-                        (int)blockIdx.x * K::CZ - K::ZS + K::EZ <= G.dim[2] - M && (int)blockIdx.y * K::CY + M + K::CY <= G.dim[1] - M;
+    const bool tma_st = OPESCI_TMA_STORE && !OPESCI_SPLIT_BARRIER && !ZF && bx > 0 &&
+                        bx * K::CZ - K::ZS + K::EZ <= G.dim[2] - M && (int)blockIdx.y * K::CY + M + K::CY <= G.dim[1] - M;
     const int xv_lo = max(xa, 2 * M + 1), xv_hi = min(xb, G.dim[0] - 2 * M - 1);
     const long long pyz = (long long)ye * G.s[1] + ze;
     const long long lv0 = (long long)A.t0 * G.level, lv1 = (long long)A.t1 * G.level;
@@ -435,6 +469,12 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     T told_buf[OPESCI_T0_AHEAD][2][6];
     long long px = (long long)xs_begin * sx;
     load_told(told_buf[0], px);
+    // ZF, high face: Tzz two columns beyond the face plane (z = dim3-1) is written by no loop, but the W update of the face
+    // plane reads it: the window must hold what the array holds (level t1).  Fetched a plane ahead like T[t0].
+    T zz_far = 0;
+    const int zf_far_lane = ZF ? ((A.zf_side[1] && bx == A.zf_bx[1]) ? ((tz == A.zf_c[1] + 2) ? 0 : (tz + 1 == A.zf_c[1] + 2) ? 1 : -1) : -1) : -1;
+    const bool zf_far = zf_far_lane >= 0 && ze + zf_far_lane < G.dim[2] && ye < G.dim[1];
+    if (ZF && zf_far) zz_far = gT1[2][px + zf_far_lane];
 #if OPESCI_T0_AHEAD == 2
     static_assert(RD % 2 == 0, "plane parity must survive the unrolled loop");
     if (xs_begin + 1 < xs_end) load_told(told_buf[1], px + sx);
@@ -632,16 +672,98 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 #pragma unroll
                 for (int k = 0; k < 6; ++k) tn[L][k] = told[L][k] + ux[L][0];
 #endif
+            // ZF: on the planes / rows of FusedArgs::zf_raw_x / zf_raw_y the plain interior Txx / Tyy go to global memory
+            // (stored here, before the z-face operations below touch the registers)
+            bool early[2] = {false, false};
+            if constexpr (ZF) {
+                early[0] = xs == A.zf_raw_x[0] || xs == A.zf_raw_x[1];
+                early[1] = ye == A.zf_raw_y[0] || ye == A.zf_raw_y[1];
+                if (xs >= xa && xs < xb) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        if (early[e]) {
+                            if (st_yz[0]) gstore(gT1[e] + px, tn[0][e]);
+                            if (st_yz[1]) gstore(gT1[e] + px + 1, tn[1][e]);
+                        }
+                }
+            }
+            if constexpr (ZF) {
+                // ---- z-face stress ghost loops of this plane, in registers (see the kernel's header comment).
+                // tn[L][k]: 0 Txx, 1 Tyy, 2 Tzz, 3 Txy, 4 Tyz, 5 Txz.  A warp is one tile row, so every source
+                // column lives in this warp: shuffles, executed by all lanes (warp-uniform branch).
+                if (zf_row && xs >= A.zf_xlo && xs < A.zf_xhi) {
+#pragma unroll
+                    for (int side = 0; side < 2; ++side) {
+                        if (!A.zf_side[side] || bx != A.zf_bx[side]) continue;    // CTA-uniform
+                        const int c = A.zf_c[side], dir = side == 0 ? -1 : 1;
+                        // Tzz[b + dir] = -Tzz[b - dir]; shear: low T[b-1] = -T[b], T[b-2] = -T[b+1]; high T[b'] = -T[b'-1],
+                        // T[b'+1] = -T[b'-2] (opesci/fields.py:355-381)
+                        const int szz = c - dir;
+                        const int dst0 = side == 0 ? c - 1 : c, src0 = side == 0 ? c : c - 1;
+                        const int dst1 = side == 0 ? c - 2 : c + 1, src1 = side == 0 ? c + 1 : c - 2;
+                        const T zz = __shfl_sync(0xffffffffu, (szz & 1) ? tn[1][2] : tn[0][2], szz >> 1);
+                        const T yz0 = __shfl_sync(0xffffffffu, (src0 & 1) ? tn[1][4] : tn[0][4], src0 >> 1);
+                        const T xz0 = __shfl_sync(0xffffffffu, (src0 & 1) ? tn[1][5] : tn[0][5], src0 >> 1);
+                        const T yz1 = __shfl_sync(0xffffffffu, (src1 & 1) ? tn[1][4] : tn[0][4], src1 >> 1);
+                        const T xz1 = __shfl_sync(0xffffffffu, (src1 & 1) ? tn[1][5] : tn[0][5], src1 >> 1);
+#pragma unroll
+                        for (int L = 0; L < 2; ++L) {
+                            const int j = tz + L;
+                            if (j == c) {
+                                // Levander: T_ee[t1] = T_ee[t0] + (bwd window of U along x) + (bwd window of V along y), emitted
+                                // order +1, -1, -2, 0 per window, separate multiply and add (face_batch evaluates the same
+                                // term table the same way in either arithmetic mode)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    T acc = told[L][e];
+                                    const float *cu = A.zf_lev[e][0], *cv = A.zf_lev[e][1];
+                                    acc = __fadd_rn(acc, __fmul_rn(cu[1], ux[L][3]));
+                                    acc = __fadd_rn(acc, __fmul_rn(-cu[0], ux[L][1]));
+                                    acc = __fadd_rn(acc, __fmul_rn(-cu[1], ux[L][0]));
+                                    acc = __fadd_rn(acc, __fmul_rn(cu[0], ux[L][2]));
+                                    acc = __fadd_rn(acc, __fmul_rn(cv[1], vy_b[L][3]));
+                                    acc = __fadd_rn(acc, __fmul_rn(-cv[0], vy_b[L][1]));
+                                    acc = __fadd_rn(acc, __fmul_rn(-cv[1], vy_b[L][0]));
+                                    acc = __fadd_rn(acc, __fmul_rn(cv[0], vy_b[L][2]));
+                                    tn[L][e] = acc;
+                                }
+                                tn[L][2] = (T)0;
+                            }
+                            if (j == c + dir) tn[L][2] = -zz;
+                            if (j == dst0) { tn[L][4] = -yz0; tn[L][5] = -xz0; }
+                            if (j == dst1) { tn[L][4] = -yz1; tn[L][5] = -xz1; }
+                            // Tzz two columns beyond the high face (z = dim3-1) is written by no loop: the W update of the
+                            // face plane reads it, so the window must hold what the array holds
+                            if (side == 1 && zf_far && L == zf_far_lane) tn[L][2] = zz_far;
+                        }
+                        // the ghost columns this plane's loops wrote (owned planes only; the interior columns go out below)
+                        if (xs >= xa && xs < xb && ty >= M && ty < M + K::CY) {
+#pragma unroll
+                            for (int L = 0; L < 2; ++L) {
+                                const int j = tz + L;
+                                if (j == c + dir) gstore(gT1[2] + px + L, tn[L][2]);
+                                if ((side == 0 && (j == dst0 || j == dst1)) || (side == 1 && j == dst1)) {
+                                    gstore(gT1[4] + px + L, tn[L][4]);
+                                    gstore(gT1[5] + px + L, tn[L][5]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
             // ---- store the new stresses (owned tile, owned planes), prefetch next T[t0]
             if (xs >= xa && xs < xb) {
                 if (st2) {
 #pragma unroll
-                    for (int k = 0; k < 6; ++k)
+                    for (int k = 0; k < 6; ++k) {
+                        if (ZF && k < 2 && early[k]) continue;
                         if (k == 0 || !tma_st) gstore2(gT1[k] + px, tn[0][k], tn[1][k]);
+                    }
                 } else {
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
                         if (k != 0 && tma_st) continue;
+                        if (ZF && k < 2 && early[k]) continue;
                         if (st_yz[0]) gstore(gT1[k] + px, tn[0][k]);
                         if (st_yz[1]) gstore(gT1[k] + px + 1, tn[1][k]);
                     }
@@ -649,6 +771,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             }
             px += sx;
             if (xs + OPESCI_T0_AHEAD < xs_end) load_told(told, px + (OPESCI_T0_AHEAD - 1) * sx);
+            if (ZF && zf_far && xs + 1 < xs_end) zz_far = gT1[2][px + zf_far_lane];
             // ---- shift the register windows, publish the in-plane operands
 #pragma unroll
             for (int L = 0; L < 2; ++L) {
@@ -711,7 +834,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                 const T *s0 = sring + (xs & (K::SR - 1)) * ST + M * K::EZ;      // first core row of the slot
 #pragma unroll
                 for (int k = 0; k < 5; ++k)
-                    tma_store_3d(&SMAPS.m[k], s0 + k * K::SR * ST, (int)blockIdx.x * K::CZ - K::ZS, (int)blockIdx.y * K::CY + M,
+                    tma_store_3d(&SMAPS.m[k], s0 + k * K::SR * ST, bx * K::CZ - K::ZS, (int)blockIdx.y * K::CY + M,
                                  A.t1 * G.dim[0] + xs);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -842,6 +965,9 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 #if OPESCI_TMA_STORE
     if (tma_st && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #endif
+    // the kernels after this one read what the z-edge grid wrote: this grid completes only after that one has
+    // (no-op when the launch has no programmatic dependency)
+    if (!ZF) asm volatile("griddepcontrol.wait;" ::: "memory");
 #if OPESCI_PACE > 0
     if (A.pace && tid == 0) A.pace[((size_t)chunk * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = 0x7fffffff;
 #endif

@@ -191,6 +191,12 @@ struct Run {
     int xs[OPESCI_MAX_CHUNKS + 1] = {};
     int zstrip = 0;                 // > 0: the fused kernel covers z < zstrip only; the thin strip [zstrip, dim-m) is done per point
     int mid0 = 0, mid1 = 0;         // slabs: chunks [mid0, mid1) read no halo plane (they overlap the halo exchange)
+    // z-fold (fused.cuh, ZF kernels): the z-face stress ghost loops and the z slabs of the velocity shell are done by the
+    // z-edge tiles of the fused kernel, launched beside the interior tiles on a second stream
+    bool zfold = false;
+    int zf_nzt = 0;                 // tile columns
+    cudaStream_t st_edge = nullptr;
+    cudaEvent_t ev_edge_fork = nullptr, ev_edge_join = nullptr;
 };
 std::map<void *, Run *> g_runs;
 std::mutex g_mu;
@@ -447,6 +453,9 @@ int sm_count()
 }
 
 // ------------------------------------------------------------------ launch helpers
+#ifndef OPESCI_ZF_SUB
+#define OPESCI_ZF_SUB 8   /* x-chunks of the z-edge launch per x-chunk of the interior launch (B200, 1024^3: 1 -> 22.19, 3 -> 21.83, 8 -> 21.63 ms per step) */
+#endif
 struct Stepper {
     const Run &R;
     cudaStream_t st;
@@ -686,17 +695,38 @@ struct Stepper {
         static const int ORDER[6] = {F_TXX, F_TYY, F_TZZ, F_TXY, F_TYZ, F_TXZ};
         static const int SH_A[3] = {0, 1, 0}, SH_B[3] = {1, 2, 2};
         const bool pair = sides_independent();
-        // sequence of loops per field
-        FaceLoop seq[6][6];
+        // sequence of loops per field; one reference loop may be cut into several disjoint pieces (z-fold strips)
+        std::vector<FaceLoop> seq[6][6];
         int nseq[6] = {0, 0, 0, 0, 0, 0};
         FaceBatch tmp;
+        // z-fold: inside planes [zx0, zx1) x rows [m+1, dim2-m-1) the z-face loops are done by the z-edge tiles of the
+        // fused kernel (fused.cuh, ZF); what is left of a [0,dim) x [0,dim) mirror loop are four thin strips
+        const bool zf = R.zfold && !init;
+        const int zx0 = M.slab.lo_face ? m + 1 : m, zx1 = M.slab.hi_face ? M.G.dim[0] - m - 1 : M.G.dim[0] - m;
+        const int zy0 = m + 1, zy1 = M.G.dim[1] - m - 1;
+        auto add_pieces = [&](std::vector<FaceLoop> &out, int field, int d, const MirrorOps &ops) {
+            tmp.count = 0;
+            if (!(zf && d == 2)) {
+                if (add_mirror(tmp, field, t1, d, ops, 0, 0)) out.push_back(tmp.loop[0]);
+                return;
+            }
+            const int box[4][4] = {{0, zx0, 0, M.G.dim[1]}, {zx1, M.G.dim[0], 0, M.G.dim[1]},
+                                   {zx0, zx1, 0, zy0}, {zx0, zx1, zy1, M.G.dim[1]}};
+            for (int k = 0; k < 4; ++k) {
+                tmp.count = 0;
+                if (!add_mirror(tmp, field, t1, d, ops, 0, 0)) continue;
+                FaceLoop L = tmp.loop[0];
+                L.lo1 = box[k][0]; L.hi1 = box[k][1]; L.lo = box[k][2]; L.hi2 = box[k][3];
+                if (L.hi1 > L.lo1 && L.hi2 > L.lo) out.push_back(L);
+            }
+        };
         for (int fi = 0; fi < 6; ++fi)
             for (int d = 0; d < 3; ++d) {
                 const int b_lo = m, b_hi = M.G.dim[d] - m - 1;
                 for (int side = 0; side < 2; ++side) {
                     tmp.count = 0;
-                    bool ok = false;
                     if (!face_present(d, side)) continue;
+                    std::vector<FaceLoop> pieces;
                     if (fi < 3 && fi == d) {
                         // own-axis normal stress (opesci/fields.py:355-381), ranges [0,dim)
                         MirrorOps ops;
@@ -704,12 +734,38 @@ struct Stepper {
                         const int b = side == 0 ? b_lo : b_hi, dir = side == 0 ? -1 : 1;
                         ops.dst[ops.count] = b; ops.src[ops.count++] = -1;
                         for (int k = 1; k <= m - 1; ++k) { ops.dst[ops.count] = b + dir * k; ops.src[ops.count++] = b - dir * k; }
-                        ok = add_mirror(tmp, ORDER[fi], t1, d, ops, 0, 0);
+                        add_pieces(pieces, ORDER[fi], d, ops);
                     } else if (fi < 3) {
                         // Levander recompute of the other normal stresses on this face from level t0
                         // (opesci/fields.py:313-353; not in the initial pass, staggeredgrid.py:771-773)
                         if (M.p.free_surface != 1 || init) continue;
-                        ok = add_equation(tmp, M.lev_stress_eq[d][fi], t0, t1, d, side == 0 ? b_lo : b_hi, m + 1, m + 1);
+                        if (!add_equation(tmp, M.lev_stress_eq[d][fi], t0, t1, d, side == 0 ? b_lo : b_hi, m + 1, m + 1)) continue;
+                        if (zf && d == 2) {
+                            // Its range IS the z-fold zone: done by the z-edge tiles -- except where an earlier loop of the
+                            // same field still has to read the plain interior value (FusedArgs::zf_raw_x): Txx on the planes
+                            // the x-face mirror reads, Tyy on the rows the y-face mirror reads.  Those lines are recomputed
+                            // here, after that mirror, as in the reference.
+                            const FaceLoop full = tmp.loop[0];
+                            if (fi == 0) {
+                                const int planes[2] = {M.slab.lo_face ? m + 1 : -1, M.slab.hi_face ? M.G.dim[0] - m - 2 : -1};
+                                for (int k = 0; k < 2; ++k) {
+                                    if (planes[k] < full.lo1 || planes[k] >= full.hi1 || (k == 1 && planes[1] == planes[0])) continue;
+                                    FaceLoop L = full;
+                                    L.lo1 = planes[k]; L.hi1 = planes[k] + 1;
+                                    pieces.push_back(L);
+                                }
+                            } else {
+                                const int rows[2] = {m + 1, M.G.dim[1] - m - 2};
+                                for (int k = 0; k < 2; ++k) {
+                                    if (rows[k] < full.lo || rows[k] >= full.hi2 || (k == 1 && rows[1] == rows[0])) continue;
+                                    FaceLoop L = full;
+                                    L.lo = rows[k]; L.hi2 = rows[k] + 1;
+                                    pieces.push_back(L);
+                                }
+                            }
+                        } else {
+                            pieces.push_back(tmp.loop[0]);
+                        }
                     } else {
                         const int a = SH_A[fi - 3], bb = SH_B[fi - 3];
                         if (d != a && d != bb) continue;
@@ -720,9 +776,10 @@ struct Stepper {
                             if (side == 0) { ops.dst[ops.count] = m - 1 - j; ops.src[ops.count++] = m + j; }
                             else { ops.dst[ops.count] = b_hi + j; ops.src[ops.count++] = b_hi - 1 - j; }
                         }
-                        ok = add_mirror(tmp, ORDER[fi], t1, d, ops, 0, 0);
+                        add_pieces(pieces, ORDER[fi], d, ops);
                     }
-                    if (ok) seq[fi][nseq[fi]++] = tmp.loop[0];
+                    // (a loop whose every piece is empty still takes its place in the sequence: the pairing below counts loops)
+                    seq[fi][nseq[fi]++] = pieces;
                 }
             }
         const int stride = pair ? 2 : 1;   // low + high side of a face pair together
@@ -730,7 +787,11 @@ struct Stepper {
             FaceBatch B;
             B.count = 0;
             for (int fi = 0; fi < 6; ++fi)
-                for (int j = k; j < k + stride && j < nseq[fi]; ++j) B.loop[B.count++] = seq[fi][j];
+                for (int j = k; j < k + stride && j < nseq[fi]; ++j)
+                    for (const FaceLoop &L : seq[fi][j]) {
+                        B.loop[B.count++] = L;
+                        if (B.count == OPESCI_MAX_BATCH) { launch_batch<T>(B); B.count = 0; }   // pieces are disjoint: any split is fine
+                    }
             launch_batch<T>(B);
         }
     }
@@ -799,9 +860,71 @@ struct Stepper {
             if (count <= 0) return;
             // z columns [M, zend) are covered by tiles; tile bx stores [bx*CZ + M - ZS, bx*CZ + M - ZS + CZ)
             const int zend = R.zstrip > 0 ? R.zstrip : Md.G.dim[2] - M;
-            dim3 grid(K::ztiles(zend + M), (Md.G.dim[1] - 2 * M + K::CY - 1) / K::CY, count);
+            const int nzt = K::ztiles(zend + M);
+            const int nyt = (Md.G.dim[1] - 2 * M + K::CY - 1) / K::CY;
             A.cluster_sync = 0;
             A.pace = nullptr;
+            // z-edge + interior launch: two streams (fork / join with events; default) or one stream with a programmatic
+            // dependency (OPESCI_ZF_PDL=1).  Measured on B200 at 1024^3: 21.50 vs 21.97 ms per step.
+            static const bool zf_pdl = getenv("OPESCI_ZF_PDL") && atoi(getenv("OPESCI_ZF_PDL")) != 0;
+            A.bx0 = 0; A.bxs[0] = A.bxs[1] = 0;
+            A.zf_side[0] = A.zf_side[1] = 0; A.zf_c[0] = A.zf_c[1] = 0; A.zf_bx[0] = A.zf_bx[1] = -1; A.zf_xlo = A.zf_xhi = 0;
+            A.zf_raw_x[0] = Md.slab.lo_face ? M + 1 : -1;
+            A.zf_raw_x[1] = Md.slab.hi_face ? Md.G.dim[0] - M - 2 : -1;
+            A.zf_raw_y[0] = M + 1; A.zf_raw_y[1] = Md.G.dim[1] - M - 2;
+            for (int e = 0; e < 2; ++e)
+                for (int f = 0; f < 2; ++f) { A.zf_lev[e][f][0] = Md.p.lev_stress[2][e][f][0]; A.zf_lev[e][f][1] = Md.p.lev_stress[2][e][f][1]; }
+            if constexpr (SO == 4) {
+                if (R.zfold) {
+                    // ---- z-edge tile columns (0 and nzt-1) on the second stream, concurrently with the interior columns
+                    FusedArgs E = A;
+                    E.zf_xlo = Md.slab.lo_face ? M + 1 : M;
+                    E.zf_xhi = Md.slab.hi_face ? Md.G.dim[0] - M - 1 : Md.G.dim[0] - M;
+                    const int c_hi = (Md.G.dim[2] - M - 1) - (nzt - 1) * K::CZ;    // tile column of the high face plane
+                    // one launch, grid.x = the z-edge tile columns: column 0 holds the low face, column nzt-1 the high one
+                    const int ne = nzt == 1 ? 1 : 2;
+                    E.bxs[0] = 0; E.bxs[1] = nzt - 1;
+                    E.zf_side[0] = E.zf_side[1] = 1;
+                    E.zf_bx[0] = 0; E.zf_bx[1] = nzt - 1;
+                    E.zf_c[0] = M; E.zf_c[1] = c_hi;
+                    // The z-edge CTAs are few (2 of nzt tile columns): cut their x-chunks finer than the interior ones, so
+                    // that their last, partly filled wave is short (a wave of full-length chunks is ~1 ms at 1024^3)
+                    static const int zf_sub_env = getenv("OPESCI_ZF_SUB") ? atoi(getenv("OPESCI_ZF_SUB")) : 0;
+                    int sub = zf_sub_env > 0 ? zf_sub_env : OPESCI_ZF_SUB;
+                    while (sub > 1 && (count * sub > OPESCI_MAX_CHUNKS || (A.xs[chunk0 + count] - A.xs[chunk0]) / (count * sub) < 16 * M)) --sub;
+                    int ecount = 0;
+                    for (int c = 0; c < count; ++c) {
+                        const int lo = A.xs[chunk0 + c], hi = A.xs[chunk0 + c + 1];
+                        for (int k = 0; k < sub; ++k) E.xs[ecount++] = lo + (int)((long long)(hi - lo) * k / sub);
+                    }
+                    E.xs[ecount] = A.xs[chunk0 + count];
+                    E.chunk0 = 0;
+                    cudaError_t e = cudaSuccess;
+                    if (!zf_pdl) {
+                        e = cudaEventRecord(R.ev_edge_fork, st);
+                        if (e == cudaSuccess) e = cudaStreamWaitEvent(R.st_edge, R.ev_edge_fork, 0);
+                        if (e != cudaSuccess && err == cudaSuccess) err = e;
+                    }
+                    static const char *zf_only_e = getenv("OPESCI_ZF_ONLY");
+                    if (!(zf_only_e && !strcmp(zf_only_e, "main")))
+                    fused_step<SO, ARITH, false, true><<<dim3(ne, nyt, ecount), K::THREADS, K::SMEM, zf_pdl ? st : R.st_edge>>>(R.tmap[0], R.tmap[1], R.tmap[2], E
+#if OPESCI_TMA_STORE
+                        , R.smaps
+#endif
+                    );
+                    check();
+                    if (!zf_pdl) {
+                        e = cudaEventRecord(R.ev_edge_join, R.st_edge);
+                        if (e != cudaSuccess && err == cudaSuccess) err = e;
+                    }
+                    A.bx0 = 1;
+                }
+            }
+            // (timing probe only, wrong results: OPESCI_ZF_ONLY=edge / main launches only one of the two kernels)
+            static const char *zf_only = getenv("OPESCI_ZF_ONLY");
+            const int nmain = (zf_only && !strcmp(zf_only, "edge")) ? 0 : R.zfold ? nzt - 2 : nzt;
+            dim3 grid(nmain > 0 ? nmain : 1, nyt, count);
+            if (nmain > 0) {
 #if OPESCI_PACE > 0
             {
                 // every tile publishes the plane it is at; a tile more than OPESCI_PACE planes ahead of a running
@@ -832,12 +955,27 @@ struct Stepper {
 #endif
 #if OPESCI_TMA_STORE
             if (Md.p.hetero) fused_step<SO, ARITH, true><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A, R.smaps);
+            else if (R.zfold && zf_pdl) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = grid; cfg.blockDim = dim3(K::THREADS); cfg.dynamicSmemBytes = K::SMEM; cfg.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                cudaError_t e = cudaLaunchKernelEx(&cfg, fused_step<SO, ARITH, false, false>, R.tmap[0], R.tmap[1], R.tmap[2], A, R.smaps);
+                if (e != cudaSuccess && err == cudaSuccess) err = e;
+            }
             else fused_step<SO, ARITH, false><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A, R.smaps);
 #else
             if (Md.p.hetero) fused_step<SO, ARITH, true><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
             else fused_step<SO, ARITH, false><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A);
 #endif
-            check();
+            }
+            if (nmain > 0) check();
+            if (R.zfold && !zf_pdl) {
+                cudaError_t e = cudaStreamWaitEvent(st, R.ev_edge_join, 0);
+                if (e != cudaSuccess && err == cudaSuccess) err = e;
+            }
             if (R.zstrip > 0) {
                 // A few z columns are left over after the last full tile (1025 = 17 x 60 + 5 at 1024^3): a whole row of
                 // nearly empty CTAs would cost as much as a full one (5.5 % of the kernel).  Their stresses are computed
@@ -867,6 +1005,7 @@ struct Stepper {
             for (int d = 0; d < 3; ++d)
                 for (int side = 0; side < 2; ++side) {
                     Range3 rg;
+                    const bool folded = R.zfold && d == 2;   // the z slabs belong to the z-edge tiles of the fused kernel
                     for (int e = 0; e < 3; ++e) {
                         if (e < d) { rg.lo[e] = ilo[e]; rg.hi[e] = ihi[e]; }     // already covered by earlier slabs
                         else if (e == d) { rg.lo[e] = side == 0 ? lo[e] : ihi[e]; rg.hi[e] = side == 0 ? ilo[e] : hi[e]; }
@@ -879,7 +1018,7 @@ struct Stepper {
                     B.nbz[nb] = nz > 0 ? (nz + tw - 1) / tw : 1;
                     B.nby[nb] = ny > 0 ? (ny + th - 1) / th : 1;
                     B.start[nb] = total;
-                    total += (nz > 0 && ny > 0 && nx > 0) ? B.nbz[nb] * B.nby[nb] * nx : 0;
+                    total += (nz > 0 && ny > 0 && nx > 0 && !folded) ? B.nbz[nb] * B.nby[nb] * nx : 0;
                     ++nb;
                 }
             B.start[6] = total;
@@ -1097,6 +1236,26 @@ int setup_fused(Run &R)
 #if OPESCI_PACE > 0
     if (!R.d_pace) CUDA_OK(cudaMalloc(&R.d_pace, (size_t)tiles * OPESCI_MAX_CHUNKS * sizeof(int)));
 #endif
+    // ---- z-fold: so = 4 with the Levander free surface, homogeneous medium.  The high face plane b' = dim3-m-1 and the
+    // columns its loops touch (b'-2 .. b'+2) must lie inside the last tile column, the z slab of the shell [b'-2, b'] in
+    // its stored columns; otherwise (last column narrower than 3 stored cells) everything stays with the face kernels.
+    R.zfold = false;
+    if (m == 2 && p.free_surface == 1 && !p.hetero && R.zstrip == 0 && !(p.flags & OPESCI_NO_ZFOLD) && !getenv("OPESCI_NO_ZFOLD")) {
+        const int c_hi = (p.dim[2] - m - 1) - (nztiles - 1) * CZ;
+        if (c_hi >= 2 * m && c_hi + 2 <= FusedCfg<2>::EZ - 1 && p.dim[1] >= 4 * m + 6 && M.G.dim[0] >= 4 * m + 6) {
+            int prio_lo = 0, prio_hi = 0;
+            CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            // higher priority: the few z-edge CTAs are scheduled as soon as they are ready instead of behind every
+            // pending CTA of the interior launch (they would otherwise form the tail of the step)
+            if (!R.st_edge) CUDA_OK(cudaStreamCreateWithPriority(&R.st_edge, cudaStreamNonBlocking, prio_hi));
+            if (!R.ev_edge_fork) CUDA_OK(cudaEventCreateWithFlags(&R.ev_edge_fork, cudaEventDisableTiming));
+            if (!R.ev_edge_join) CUDA_OK(cudaEventCreateWithFlags(&R.ev_edge_join, cudaEventDisableTiming));
+            CUDA_OK(cudaFuncSetAttribute(fused_step<4, OPESCI_ARITH_REFERENCE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<2>::SMEM));
+            CUDA_OK(cudaFuncSetAttribute(fused_step<4, OPESCI_ARITH_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<2>::SMEM));
+            R.zfold = true;
+            R.zf_nzt = nztiles;
+        }
+    }
     R.fused = true;
     return 0;
 }
@@ -1410,6 +1569,9 @@ void release(Run *R)
     if (R->d_src) cudaFree(R->d_src);
     if (R->d_step) cudaFree(R->d_step);
     if (R->d_pace) cudaFree(R->d_pace);
+    if (R->ev_edge_fork) cudaEventDestroy(R->ev_edge_fork);
+    if (R->ev_edge_join) cudaEventDestroy(R->ev_edge_join);
+    if (R->st_edge) cudaStreamDestroy(R->st_edge);
     delete R;
 }
 

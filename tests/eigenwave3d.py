@@ -160,13 +160,17 @@ def converge_test(execute=True):
     s = 10
     c = 0.4 * s
     results = []
+    tmp_dir = path.join(path.dirname(path.abspath(__file__)), 'tmp')    # the reference writes into ./tmp
+    os.makedirs(tmp_dir, exist_ok=True)
     for _ in range(4):
         dt = c / (s ** 2)
+        filename = path.join(tmp_dir, 'test3d_' + str(s) + '.json')
         grid = eigenwave3d(domain_size, (s, s, s), dt, 5.0, o_converge=True, accuracy_order=[2, 4, 4, 4],
-                           filename='tmp/test3d_' + str(s) + '.json')
+                           filename=filename)
         if execute:
-            grid.execute('tmp/test3d_' + str(s) + '.json')
+            grid.execute(filename)
             results.append((s, grid.convergence()))
+            grid.free()
         s = s * 2
     return results
 
