@@ -524,6 +524,73 @@ face_batch(const __grid_constant__ FieldPtrs F, const __grid_constant__ GridGeom
     }
 }
 
+// ---- velocity ghost loops of the two z faces (Levander, so = 4, homogeneous medium) in ONE launch.
+// Reference: opesci/staggeredgrid.py:815-864 emits, per z face, the W loop (W is staggered along z) and then the U and
+// V loops, which read the W ghosts the first loop has just written at (x+1, y) and (x, y+1) -- two dependent launches
+// through face_batch.  Every cell of these loops touches one 32-byte sector at the end of a 4-KB row, so the launches
+// are bound by DRAM sectors, and the second launch fetches again what the first one had.  Here one thread owns one
+// (x, y) column end and evaluates the W-ghost expression three times -- for itself and for its +x and +y neighbours,
+// with exactly the operands and the operation order those neighbours use, so the values are the ones they store --
+// then the U and V expressions: every sector is fetched once.  Term order and literals are those of
+// build_levander (opesci_b200.cu), i.e. of the emitted C++ (opesci/fields.py:208-242).
+struct VelZFaceArgs {
+    float cn[2];     // lev_vnormal[2][0], [2][1]  (r * dx3/dx1, r * dx3/dx2)
+    float gt[2];     // lev_vtang[2][0], [2][1]    (dx3/dx1, dx3/dx2)
+    int x0, x1, y0, y1;   // loop ranges of all six loops: [1, dim-1) on x and y
+    int m, dimz;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) vel_zface_lev(FieldPtrs F, GridGeom G, long long lvl, VelZFaceArgs A)
+{
+    const int y = A.y0 + blockIdx.x * 32 + (int)(threadIdx.x & 31);
+    const int x = A.x0 + blockIdx.y * 8 + (int)(threadIdx.x >> 5);
+    const int side = blockIdx.z;
+    if (x >= A.x1 || y >= A.y1) return;
+    T *U = (T *)F.f[F_U] + lvl, *V = (T *)F.f[F_V] + lvl, *W = (T *)F.f[F_W] + lvl;
+    const long long sx = G.s[0], sy = G.s[1];
+    const int m = A.m;
+    const T sg = side == 0 ? (T)1 : (T)-1;
+    const int nw = side == 0 ? m - 1 : A.dimz - m - 1;          // W ghost plane
+    const int zp = side == 0 ? nw + 1 : nw;                     // plane of the tangential differences
+    const int zs = side == 0 ? nw + 1 : nw - 1;                 // W[n +- 1]
+    const T c0 = (T)(-sg * A.cn[0]), c0p = (T)(sg * A.cn[0]), c1 = (T)(-sg * A.cn[1]), c1p = (T)(sg * A.cn[1]);
+    auto wghost = [&](int xx, int yy) -> T {
+        const long long q = (long long)xx * sx + (long long)yy * sy;
+        T acc = mul_rn<T>(c0, U[q - sx + zp]);
+        acc = add_rn<T>(acc, mul_rn<T>(c0p, U[q + zp]));
+        acc = add_rn<T>(acc, mul_rn<T>(c1, V[q - sy + zp]));
+        acc = add_rn<T>(acc, mul_rn<T>(c1p, V[q + zp]));
+        acc = add_rn<T>(acc, W[q + zs]);
+        return acc;
+    };
+    auto in_range = [&](int xx, int yy) { return xx >= A.x0 && xx < A.x1 && yy >= A.y0 && yy < A.y1; };
+    const long long q = (long long)x * sx + (long long)y * sy;
+    const T wg = wghost(x, y);
+    // W ghosts of the +x / +y neighbours: what their own threads store, or -- outside the W loop's range -- what the array holds
+    const T wg_xp = in_range(x + 1, y) ? wghost(x + 1, y) : W[q + sx + nw];
+    const T wg_yp = in_range(x, y + 1) ? wghost(x, y + 1) : W[q + sy + nw];
+    const int nu = side == 0 ? m - 1 : A.dimz - m;               // U, V ghost plane
+    const int pl1 = side == 0 ? 1 : -2, sf0 = side == 0 ? 1 : -1, sf1 = side == 0 ? 2 : -2;
+    const T two = (T)2.0f;
+    T out[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const T *Ve = e == 0 ? U : V;
+        const long long se = e == 0 ? sx : sy;
+        const T g = (T)(sg * A.gt[e]), gn = (T)(-sg * A.gt[e]);
+        T acc = mul_rn<T>(two, Ve[q + nu + sf0]);
+        acc = add_rn<T>(acc, -Ve[q + nu + sf1]);
+        acc = add_rn<T>(acc, mul_rn<T>(g, e == 0 ? wg_xp : wg_yp));
+        acc = add_rn<T>(acc, mul_rn<T>(gn, W[q + se + nu + pl1]));
+        acc = add_rn<T>(acc, mul_rn<T>(gn, wg));
+        acc = add_rn<T>(acc, mul_rn<T>(g, W[q + nu + pl1]));
+        out[e] = acc;
+    }
+    W[q + nw] = wg;
+    U[q + nu] = out[0];
+    V[q + nu] = out[1];
+}
+
 // ------------------------------------------------------------------ point source + receivers
 // Semantics of the reference's hand-written propagator (tests/src/test_ref_iso_elastic.cpp:227-290), run at the end of
 // a time step: receivers sample U, V, W and the mean normal stress of the new level; then the explosive source is

@@ -807,6 +807,18 @@ struct Stepper {
         FaceBatch robertsson;
         robertsson.count = 0;
         for (int d = 0; d < 3; ++d) {
+            if (d == 2 && M.p.free_surface == 1 && !M.p.hetero && pair && !(M.p.flags & OPESCI_NO_ZFOLD)) {
+                // both z faces, all three components, one launch (kernels.cuh: vel_zface_lev)
+                VelZFaceArgs A;
+                A.cn[0] = M.p.lev_vnormal[2][0]; A.cn[1] = M.p.lev_vnormal[2][1];
+                A.gt[0] = M.p.lev_vtang[2][0]; A.gt[1] = M.p.lev_vtang[2][1];
+                A.x0 = 1; A.x1 = M.G.dim[0] - 1; A.y0 = 1; A.y1 = M.G.dim[1] - 1;
+                A.m = m; A.dimz = M.G.dim[2];
+                dim3 grid((A.y1 - A.y0 + 31) / 32, (A.x1 - A.x0 + 7) / 8, 2);
+                vel_zface_lev<T><<<grid, 256, 0, st>>>(ptrs(), M.G, (long long)t1 * M.G.level, A);
+                check();
+                continue;
+            }
             int seq[3];
             seq[0] = d;
             for (int k = 0, n = 1; k < 3; ++k)
