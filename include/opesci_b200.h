@@ -183,7 +183,8 @@ typedef struct OpesciB200Params {
     int32_t hetero;
     int32_t media_plane0;            /* global index of the first x plane held by rho/vp/vs ... */
     int32_t media_nplanes;           /* ... and how many planes they hold (whole array: 0, dim1) */
-    int32_t reserved_;
+    int32_t fs_faces;            /* bit (2*d + side) set: face (axis d = 0..2, side 0 low / 1 high) carries the free-surface
+                                  * treatment (set_free_surface_boundary, staggeredgrid.py:214-232); 0 = all six */
     const float *rho, *vp, *vs;      /* HOST arrays [media_nplanes][dim2][dim3]: the flat float32 layout the
                                       * reference's raw-binary reader expects: opesci/staggeredgrid.py:549-551 */
     float h_c[3][OPESCI_MAX_M];      /* [axis d][k-1]: c_k*dt/dx_d */
@@ -242,6 +243,11 @@ int opesci_b200_last_timing(double *loop_seconds, double *points_per_step, int64
  * out_ms[0] = stress (or fused stress+velocity) kernel, out_ms[1] = velocity kernel (0 if fused),
  * out_ms[2] = all ghost-cell loops of one step.  Advances the fields; call it last. */
 int opesci_b200_time_kernels(OpesciGrid *grid, int reps, double *out_ms);
+/* z-fold runs (so = 4, homogeneous: the fused step is two concurrent launches): device time of each launch on its own,
+ * out[0] = interior tile columns, out[1] = the two z-edge tile columns (ms), out[2] = interior z columns the interior
+ * launch stores, out[3] = all interior z columns.  All zeros when the fused step is a single launch.  Results of the
+ * timing launches are wrong by construction (each skips the other's cells): call it last, like time_kernels. */
+int opesci_b200_time_fused_parts(OpesciGrid *grid, int reps, double *out);
 /* Host result arrays (OPESCI_HOST_MIRROR_FULL) come from a process-wide pool of page-locked blocks that
  * outlives opesci_free; reserve_host pre-fills it with `count` blocks of `bytes_per_array`
  * (page-locking tens of GB takes far longer than copying them), release_host frees the unused blocks. */

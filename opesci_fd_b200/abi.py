@@ -84,7 +84,7 @@ class OpesciB200Params(Structure):
         ("ac_init_coef", (c_float * OPESCI_MAX_M) * 3),
         ("ac_init_centre", c_float),
         ("ac_init_const", c_double),
-        ("hetero", c_int32), ("media_plane0", c_int32), ("media_nplanes", c_int32), ("reserved_", c_int32),
+        ("hetero", c_int32), ("media_plane0", c_int32), ("media_nplanes", c_int32), ("fs_faces", c_int32),
         ("rho", POINTER(c_float)), ("vp", POINTER(c_float)), ("vs", POINTER(c_float)),
         ("h_c", (c_float * OPESCI_MAX_M) * 3),
         ("h_c2", (c_float * OPESCI_MAX_M) * 3),
@@ -106,7 +106,7 @@ EXPORTED_SYMBOLS = [
     "opesci_b200_is_cuda", "opesci_b200_time_kernels",
     "opesci_b200_comm_unique_id", "opesci_b200_comm_init", "opesci_b200_comm_finalize",
     "opesci_b200_reserve_host", "opesci_b200_release_host", "opesci_b200_slab_range",
-    "opesci_b200_execute_loopback",
+    "opesci_b200_execute_loopback", "opesci_b200_time_fused_parts",
 ]
 # include/opesci_io.h (model input / field output around the path)
 IO_SYMBOLS = [
@@ -142,6 +142,9 @@ def bind(lib):
     if hasattr(lib, "opesci_b200_time_kernels"):
         lib.opesci_b200_time_kernels.argtypes = [POINTER(OpesciGrid), ctypes.c_int, POINTER(c_double)]
         lib.opesci_b200_time_kernels.restype = ctypes.c_int
+    if hasattr(lib, "opesci_b200_time_fused_parts"):
+        lib.opesci_b200_time_fused_parts.argtypes = [POINTER(OpesciGrid), ctypes.c_int, POINTER(c_double)]
+        lib.opesci_b200_time_fused_parts.restype = ctypes.c_int
     if hasattr(lib, "opesci_b200_reserve_host"):
         lib.opesci_b200_reserve_host.argtypes = [ctypes.c_size_t, ctypes.c_int]
         lib.opesci_b200_reserve_host.restype = ctypes.c_int

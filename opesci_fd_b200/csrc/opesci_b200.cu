@@ -475,6 +475,7 @@ struct Stepper {
         for (int k = 0; k < OPESCI_MEDIA_COUNT; ++k) MD.m[k] = R.media[k];
         return MD;
     }
+    int fused_part = 0;   // timing only (opesci_b200_time_fused_parts): 1 = interior launch only, 2 = z-edge launch only
     void check()
     {
         cudaError_t e = cudaGetLastError();
@@ -668,8 +669,12 @@ struct Stepper {
         return true;
     }
     // x-face loops exist only where the slab end is a physical face
+    // a face takes part if set_free_surface_boundary was called for it (opesci/staggeredgrid.py:214-232, 766-768) and,
+    // along x, if this slab holds the physical face
     bool face_present(int d, int side) const
     {
+        const int mask = R.M.p.fs_faces ? R.M.p.fs_faces : 63;
+        if (R.M.p.free_surface == 0 || !((mask >> (2 * d + side)) & 1)) return false;
         return d != 0 || (side == 0 ? R.M.slab.lo_face : R.M.slab.hi_face);
     }
     // low and high side of one face pair never touch the same cells once the grid is this large
@@ -807,7 +812,7 @@ struct Stepper {
         FaceBatch robertsson;
         robertsson.count = 0;
         for (int d = 0; d < 3; ++d) {
-            if (d == 2 && M.p.free_surface == 1 && !M.p.hetero && pair && !(M.p.flags & OPESCI_NO_ZFOLD)) {
+            if (d == 2 && M.p.free_surface == 1 && !M.p.hetero && pair && !(M.p.flags & OPESCI_NO_ZFOLD) && face_present(2, 0) && face_present(2, 1)) {
                 // both z faces, all three components, one launch (kernels.cuh: vel_zface_lev)
                 VelZFaceArgs A;
                 A.cn[0] = M.p.lev_vnormal[2][0]; A.cn[1] = M.p.lev_vnormal[2][1];
@@ -917,8 +922,7 @@ struct Stepper {
                         if (e == cudaSuccess) e = cudaStreamWaitEvent(R.st_edge, R.ev_edge_fork, 0);
                         if (e != cudaSuccess && err == cudaSuccess) err = e;
                     }
-                    static const char *zf_only_e = getenv("OPESCI_ZF_ONLY");
-                    if (!(zf_only_e && !strcmp(zf_only_e, "main")))
+                    if (fused_part != 1)
                     fused_step<SO, ARITH, false, true><<<dim3(ne, nyt, ecount), K::THREADS, K::SMEM, zf_pdl ? st : R.st_edge>>>(R.tmap[0], R.tmap[1], R.tmap[2], E
 #if OPESCI_TMA_STORE
                         , R.smaps
@@ -932,9 +936,7 @@ struct Stepper {
                     A.bx0 = 1;
                 }
             }
-            // (timing probe only, wrong results: OPESCI_ZF_ONLY=edge / main launches only one of the two kernels)
-            static const char *zf_only = getenv("OPESCI_ZF_ONLY");
-            const int nmain = (zf_only && !strcmp(zf_only, "edge")) ? 0 : R.zfold ? nzt - 2 : nzt;
+            const int nmain = fused_part == 2 ? 0 : R.zfold ? nzt - 2 : nzt;
             dim3 grid(nmain > 0 ? nmain : 1, nyt, count);
             if (nmain > 0) {
 #if OPESCI_PACE > 0
@@ -1252,7 +1254,9 @@ int setup_fused(Run &R)
     // columns its loops touch (b'-2 .. b'+2) must lie inside the last tile column, the z slab of the shell [b'-2, b'] in
     // its stored columns; otherwise (last column narrower than 3 stored cells) everything stays with the face kernels.
     R.zfold = false;
-    if (m == 2 && p.free_surface == 1 && !p.hetero && R.zstrip == 0 && !(p.flags & OPESCI_NO_ZFOLD) && !getenv("OPESCI_NO_ZFOLD")) {
+    const int fs_mask = p.fs_faces ? p.fs_faces : 63;
+    if (m == 2 && p.free_surface == 1 && !p.hetero && R.zstrip == 0 && !(p.flags & OPESCI_NO_ZFOLD) && !getenv("OPESCI_NO_ZFOLD") &&
+        ((fs_mask >> 4) & 3) == 3) {   // both z faces carry the free surface
         const int c_hi = (p.dim[2] - m - 1) - (nztiles - 1) * CZ;
         if (c_hi >= 2 * m && c_hi + 2 <= FusedCfg<2>::EZ - 1 && p.dim[1] >= 4 * m + 6 && M.G.dim[0] >= 4 * m + 6) {
             int prio_lo = 0, prio_hi = 0;
@@ -1516,11 +1520,12 @@ int dispatch(Run &R, cudaStream_t st, double *secs)
     return fast ? dispatch_so<float, OPESCI_ARITH_FAST>(R, st, secs) : dispatch_so<float, OPESCI_ARITH_REFERENCE>(R, st, secs);
 }
 
-template <int SO, typename T, int ARITH> int time_kernels_impl(Run &R, int reps, double *out_ms)
+template <int SO, typename T, int ARITH> int time_kernels_impl(Run &R, int reps, double *out_ms, int part = 0)
 {
     cudaStream_t st;
     CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     Stepper S(R, st);
+    S.fused_part = part;
     cudaEvent_t e0, e1;
     CUDA_OK(cudaEventCreate(&e0));
     CUDA_OK(cudaEventCreate(&e1));
@@ -1528,7 +1533,7 @@ template <int SO, typename T, int ARITH> int time_kernels_impl(Run &R, int reps,
     out_ms[0] = out_ms[1] = out_ms[2] = 0.0;
     float ms;
     for (int phase = 0; phase < 3; ++phase) {
-        if (!staggered && phase > 0) break;
+        if ((!staggered || part != 0) && phase > 0) break;
         CUDA_OK(cudaStreamSynchronize(st));
         CUDA_OK(cudaEventRecord(e0, st));
         for (int r = 0; r < reps; ++r) {
@@ -1553,8 +1558,9 @@ template <int SO, typename T, int ARITH> int time_kernels_impl(Run &R, int reps,
     cudaStreamDestroy(st);
     return 0;
 }
-template <typename T, int ARITH> int time_kernels_so(Run &R, int reps, double *out_ms)
+template <typename T, int ARITH> int time_kernels_so(Run &R, int reps, double *out_ms, int part = 0)
 {
+    if (part != 0) return R.M.p.so == 4 ? time_kernels_impl<4, T, ARITH>(R, reps, out_ms, part) : fail("fused parts: so = 4 only");
     switch (R.M.p.so) {
     case 2: return time_kernels_impl<2, T, ARITH>(R, reps, out_ms);
     case 4: return time_kernels_impl<4, T, ARITH>(R, reps, out_ms);
@@ -2136,6 +2142,26 @@ int opesci_b200_time_kernels(OpesciGrid *grid, int reps, double *out_ms)
     if (R->M.p.is_double)
         return fast ? time_kernels_so<double, OPESCI_ARITH_FAST>(*R, reps, out_ms) : time_kernels_so<double, OPESCI_ARITH_REFERENCE>(*R, reps, out_ms);
     return fast ? time_kernels_so<float, OPESCI_ARITH_FAST>(*R, reps, out_ms) : time_kernels_so<float, OPESCI_ARITH_REFERENCE>(*R, reps, out_ms);
+}
+
+int opesci_b200_time_fused_parts(OpesciGrid *grid, int reps, double *out)
+{
+    Run *R = find_run(grid);
+    if (!R) return fail("opesci_b200_time_fused_parts: unknown grid");
+    out[0] = out[1] = out[2] = out[3] = 0.0;
+    if (!R->fused || !R->zfold || R->M.p.is_double) return 0;     // one launch: opesci_b200_time_kernels covers it
+    if (reps < 1) reps = 1;
+    const bool fast = (R->M.p.flags & OPESCI_ARITH_MASK) == OPESCI_ARITH_FAST;
+    double ms[3];
+    for (int part = 1; part <= 2; ++part) {
+        if (fast ? time_kernels_so<float, OPESCI_ARITH_FAST>(*R, reps, ms, part) : time_kernels_so<float, OPESCI_ARITH_REFERENCE>(*R, reps, ms, part)) return 1;
+        out[part - 1] = ms[0];
+    }
+    // interior z columns stored by the interior launch (tile columns 1 .. nzt-2) and by both launches together
+    const int m = R->M.m, CZ = FusedCfg<2>::CZ;
+    out[2] = (double)(R->zf_nzt > 2 ? (R->zf_nzt - 2) * CZ : 0);
+    out[3] = (double)(R->M.p.dim[2] - 2 * m);
+    return 0;
 }
 
 int opesci_b200_comm_unique_id(void *out_id, int nbytes)

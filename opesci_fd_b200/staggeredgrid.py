@@ -298,9 +298,9 @@ class StaggeredGrid(RegularGrid):
     def build_params(self):
         if not getattr(self, 'pde', None):
             raise RuntimeError("solve_fd() must be called before the model can be lowered")
-        if self._free_surface != {(d, s) for d in (1, 2, 3) for s in (0, 1)}:
-            raise NotImplementedError("all six faces must be free surfaces "
-                                      "(set_free_surface_boundary(dimension=1..3, side=0..1))")
+        for (d, s_) in self._free_surface:
+            if d not in (1, 2, 3) or s_ not in (0, 1):
+                raise ValueError("set_free_surface_boundary(dimension=1..3, side=0..1)")
         if len(set(self.order[1:])) != 1:
             raise NotImplementedError("equal spatial order on all axes required")
         if self.order[0] != 2:
@@ -310,7 +310,10 @@ class StaggeredGrid(RegularGrid):
         m = so // 2
         vel, normal, shear = self._slot_fields()
         p = self._common_params(abi.KIND_STAGGERED_ELASTIC, 9, 2)
-        p.free_surface = abi.FS_LEVANDER if so == 4 else abi.FS_ROBERTSSON
+        # any subset of the six faces (reference: one set_free_surface_boundary call per face, staggeredgrid.py:214-232;
+        # faces without a call get no boundary loops, :766-768)
+        p.fs_faces = sum(1 << (2 * (d - 1) + s_) for (d, s_) in self._free_surface)
+        p.free_surface = abi.FS_NONE if not self._free_surface else (abi.FS_LEVANDER if so == 4 else abi.FS_ROBERTSSON)
         ck = staggered_first_weights(m)
         dt = _frac(self.dt.value)
         dx = [None] + [_frac(sp.value) for sp in self.spacing]

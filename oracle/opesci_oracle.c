@@ -673,6 +673,7 @@ int opesci_b200_slab_range(int rank, int nranks, int gdim1, int so, int *L0, int
     if (L1) *L1 = sl.L1;
     return 0;
 }
+int opesci_b200_time_fused_parts(OpesciGrid *grid, int reps, double *out) { (void)grid; (void)reps; (void)out; return fail("opesci_b200_time_fused_parts: CUDA library only"); }
 int opesci_b200_execute_loopback(int nranks, OpesciGrid *grids) { (void)nranks; (void)grids; return fail("opesci_b200_execute_loopback: CUDA library only"); }
 int opesci_b200_reserve_host(size_t bytes_per_array, int count) { (void)bytes_per_array; (void)count; return 0; }
 int opesci_b200_release_host(void) { return 0; }

@@ -42,6 +42,8 @@ def make_grid(cfg, flags=None):
         g = drv.eigenwave3d(tuple(cfg["domain"]), tuple(cfg["grid_size"]), cfg["dt"], cfg["dt"] * cfg["steps"],
                             accuracy_order=order, o_converge=True, double=cfg["double"],
                             rho=cfg.get("rho", 1.0), vp=cfg.get("vp", 1.0), vs=cfg.get("vs", 0.5), verbose=False)
+        if "faces" in cfg:   # free surfaces on a subset of the faces (the driver sets all six)
+            g._free_surface = {tuple(f) for f in cfg["faces"]}
     else:
         import simplewaveequation as drv
         g = drv.simplewave3d(tuple(cfg["domain"]), tuple(cfg["grid_size"]), cfg["dt"], cfg["dt"] * cfg["steps"],

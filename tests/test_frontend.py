@@ -151,7 +151,14 @@ def test_unsupported_models_raise():
     with pytest.raises((IOError, OSError)):
         h.build_params()
     g = drv.eigenwave3d((1.0, 1.0, 1.0), (10, 10, 10), 0.002, 0.01, accuracy_order=[2, 4, 4, 4], verbose=False)
+    # any subset of the six faces is accepted (reference: one set_free_surface_boundary call per face)
     g._free_surface.discard((3, 1))
+    p, keep = g.build_params()
+    assert p.fs_faces == 63 - (1 << 5) and p.free_surface == abi.FS_LEVANDER
+    g._free_surface.clear()
+    p, keep = g.build_params()
+    assert p.fs_faces == 0 and p.free_surface == abi.FS_NONE
+    g.set_order([2, 4, 8, 4])
     with pytest.raises(NotImplementedError):
         g.build_params()
 

@@ -41,7 +41,8 @@ def test_oracle_bit_exact_vs_reference_golden(name, oracle_lib):
     grid.free()
 
 
-@pytest.mark.parametrize("name", sorted(HASHES))
+# (the 512^3 and so=8 256^3 entries are GPU-side fixtures: minutes on the CPU oracle; the 256^3 x 40-step one stays, ~1 min)
+@pytest.mark.parametrize("name", sorted(n for n in HASHES if HASHES[n]["config"]["kind"] == "eigenwave3d_read" or n == "ew_large_so4_f32_n256"))
 def test_oracle_bit_exact_vs_patched_reference_hashes(name, oracle_lib):
     """Heterogeneous `read` mode at 48x40x44 cells x 40 steps (random rho/vp/vs per cell): the fields are too
     large to commit, so the fixture holds the sha256 of the raw bits of every field as produced by the
