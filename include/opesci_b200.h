@@ -114,7 +114,8 @@ typedef struct OpesciFieldSpec {
                                   * L2 = sqrt(volume_literal * sum residual^2) */
 } OpesciFieldSpec;
 
-enum { OPESCI_KIND_STAGGERED_ELASTIC = 1, OPESCI_KIND_REGULAR_ACOUSTIC = 2 };
+enum { OPESCI_KIND_STAGGERED_ELASTIC = 1, OPESCI_KIND_REGULAR_ACOUSTIC = 2,
+       OPESCI_KIND_REGULAR_GENERIC = 3 /* any PDE system on a RegularGrid: kernels compiled at run time (generic_source) */ };
 
 /* flags */
 enum {
@@ -214,6 +215,16 @@ typedef struct OpesciB200Params {
     void *receiver_out;               /* HOST [ntsteps][4][n_receivers] real_t, filled by opesci_execute */
 
     OpesciFieldSpec fields[OPESCI_MAX_FIELDS];
+
+    /* ---- OPESCI_KIND_REGULAR_GENERIC (reference: opesci/regulargrid.py:230-270, 530-619).
+     * CUDA C++ source defining
+     *   extern "C" __global__ void opesci_generic_step (real_t *f0, ..., real_t *f{nfields-1}, int _t0, int _t1, int _t2);
+     *   extern "C" __global__ void opesci_generic_init2(real_t *f0, ..., real_t *f{nfields-1}, int _t0, int _t1);
+     * one thread per interior point (blocks of 64 x 4 threads along z, y; blockIdx.z = plane - m), arrays indexed as
+     * [level][dim1][dim2][pitch] with pitch = dim3 rounded up to a multiple of 32.  The host front end prints into it the
+     * expressions the reference's generator emits for the same PDEs; the library compiles it for sm_100a with NVRTC
+     * (`--fmad=false` in reference arithmetic).  nlevels must be 3; no slabs. */
+    const char *generic_source;
 } OpesciB200Params;
 
 /* ---- entry points ---------------------------------------------------------------------- */

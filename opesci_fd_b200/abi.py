@@ -21,6 +21,7 @@ MEDIA_NAMES = ['beta', 'lambda', 'mu', 'beta1', 'beta2', 'beta3', 'mu12', 'mu13'
 
 KIND_STAGGERED_ELASTIC = 1
 KIND_REGULAR_ACOUSTIC = 2
+KIND_REGULAR_GENERIC = 3
 
 ARITH_REFERENCE = 0
 ARITH_FAST = 1
@@ -97,6 +98,7 @@ class OpesciB200Params(Structure):
         ("src_x", POINTER(c_float)), ("src_y", POINTER(c_float)), ("src_z", POINTER(c_float)),
         ("receiver_out", c_void_p),
         ("fields", OpesciFieldSpec * OPESCI_MAX_FIELDS),
+        ("generic_source", c_char_p),
     ]
 
 

@@ -26,6 +26,8 @@ def literal_text(value):
     mant = mant.rstrip('0')
     if mant.endswith('.'):
         mant += '0'
+    if int(exp) == 0:
+        return mant              # mpmath's to_str omits a zero exponent: `1.988074375F`
     return '%se%d' % (mant, int(exp))
 
 

@@ -29,6 +29,7 @@
 
 #include "../../include/opesci_slab.h"
 #include "fused.cuh"
+#include "generic.cuh"
 #include "hetero.cuh"
 #include "io.cuh"
 #include "kernels.cuh"
@@ -158,6 +159,7 @@ struct Model {
     std::vector<double> tables;                  // host copy of every table
     std::vector<size_t> table_off[OPESCI_MAX_FIELDS][2];
     OpesciSlab slab;                              // x-slab of this rank (whole domain when nranks == 1)
+    std::string generic_source;                   // OPESCI_KIND_REGULAR_GENERIC: private copy of the CUDA source
 };
 Model g_model;
 
@@ -191,6 +193,7 @@ struct Run {
     int xs[OPESCI_MAX_CHUNKS + 1] = {};
     int zstrip = 0;                 // > 0: the fused kernel covers z < zstrip only; the thin strip [zstrip, dim-m) is done per point
     int mid0 = 0, mid1 = 0;         // slabs: chunks [mid0, mid1) read no halo plane (they overlap the halo exchange)
+    opesci_generic::Module gen;     // OPESCI_KIND_REGULAR_GENERIC: the NVRTC-compiled kernels of this model
     // z-fold (fused.cuh, ZF kernels): the z-face stress ghost loops and the z slabs of the velocity shell are done by the
     // z-edge tiles of the fused kernel, launched beside the interior tiles on a second stream
     bool zfold = false;
@@ -783,8 +786,10 @@ struct Stepper {
                         }
                         add_pieces(pieces, ORDER[fi], d, ops);
                     }
-                    // (a loop whose every piece is empty still takes its place in the sequence: the pairing below counts loops)
-                    seq[fi][nseq[fi]++] = pieces;
+                    // slot = face: launch k holds the loops of face k of every field, so the low / high pairing below always
+                    // pairs the two sides of ONE axis, also when some faces carry no free surface
+                    seq[fi][2 * d + side] = pieces;
+                    nseq[fi] = 6;
                 }
             }
         const int stride = pair ? 2 : 1;   // low + high side of a face pair together
@@ -1075,8 +1080,25 @@ struct Stepper {
         }
         point_hooks<T>(t1);
     }
+    // OPESCI_KIND_REGULAR_GENERIC (generic.cuh): the run-time compiled kernels, one thread per interior point
+    void generic_launch(CUfunction f, const int *levels, int nlevels)
+    {
+        const Model &M = R.M;
+        const int m = M.m;
+        if (!opesci_generic::launch(f, R.dev, M.p.nfields, levels, nlevels, M.G.dim[2] - 2 * m, M.G.dim[1] - 2 * m, M.G.dim[0] - 2 * m, st) &&
+            err == cudaSuccess)
+            err = cudaErrorLaunchFailure;
+        check();
+    }
+    void generic_step(int ti)
+    {
+        const int t0 = ti % 3, t1 = (t0 + 1) % 3, t2 = (t1 + 1) % 3;   // opesci/regulargrid.py:408-433
+        const int lv[3] = {t0, t1, t2};
+        generic_launch(R.gen.step, lv, 3);
+    }
     template <int SO, typename T, int ARITH> void acoustic_step(int ti)
     {
+        if (R.M.p.kind == OPESCI_KIND_REGULAR_GENERIC) { generic_step(ti); return; }
         const int t0 = ti % 3, t1 = (t0 + 1) % 3, t2 = (t1 + 1) % 3;
         acoustic<SO, T, ARITH>(t0, t1, t2, false);
     }
@@ -1300,6 +1322,11 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     if (staggered) {
         S.template stress_bc<T>(0, 0, true);   // initialise_bc (staggeredgrid.py:866-879)
         S.template velocity_bc<T>(0);
+    } else if (p.kind == OPESCI_KIND_REGULAR_GENERIC) {
+        // second initialisation of every field (regulargrid.py:530-564; the reference emits it once per field --
+        // it reads level 0 only, so once is the same)
+        const int lv[2] = {0, 1};
+        S.generic_launch(R.gen.init2, lv, 2);
     } else {
         S.template acoustic<SO, T, ARITH>(0, 0, 1, true);   // second initialisation: level 1 from level 0
     }
@@ -1587,6 +1614,7 @@ void release(Run *R)
     if (R->d_src) cudaFree(R->d_src);
     if (R->d_step) cudaFree(R->d_step);
     if (R->d_pace) cudaFree(R->d_pace);
+    opesci_generic::unload(R->gen);
     if (R->ev_edge_fork) cudaEventDestroy(R->ev_edge_fork);
     if (R->ev_edge_join) cudaEventDestroy(R->ev_edge_join);
     if (R->st_edge) cudaStreamDestroy(R->st_edge);
@@ -1950,6 +1978,12 @@ int opesci_b200_configure(const OpesciB200Params *params)
             if (params->so != 4) return fail("Levander free surface needs so == 4");
             if (params->hetero) build_levander_hetero(M); else build_levander(M);
         }
+    } else if (params->kind == OPESCI_KIND_REGULAR_GENERIC) {
+        if (params->nfields < 1 || params->nfields > OPESCI_MAX_FIELDS || params->nlevels != 3) return fail("generic PDEs: 1..9 fields, 3 time levels");
+        if (!params->generic_source || !*params->generic_source) return fail("generic PDEs: generic_source is empty");
+        if (nranks > 1) return fail("generic PDEs: x-slabs are not supported");
+        M.generic_source = params->generic_source;
+        M.p.generic_source = nullptr;    // the caller's string need not outlive this call
     } else if (params->kind == OPESCI_KIND_REGULAR_ACOUSTIC) {
         if (params->nfields != 1 || params->nlevels != 3) return fail("regular: need 1 field, 3 levels");
     } else {
@@ -1987,6 +2021,15 @@ static int execute_model(const Model &model, OpesciGrid *grid, OpesciProfiling *
     if (setup_fused(*R)) return bail(1);
     if (setup_tiled(*R)) return bail(1);
     if (setup_hooks(*R)) return bail(1);
+    if (p.kind == OPESCI_KIND_REGULAR_GENERIC) {
+        const bool fast = (p.flags & OPESCI_ARITH_MASK) == OPESCI_ARITH_FAST;
+        std::string detail;
+        if (const char *e = opesci_generic::compile(R->M.generic_source, fast, R->gen, detail)) {
+            static thread_local std::string msg;
+            msg = detail.substr(0, 700);
+            return bail(fail("%s: %s", e, msg.c_str()));
+        }
+    }
     double secs = 0.0;
     if (dispatch(*R, st, &secs)) return bail(1);
     if (!tl_loop || model.slab.rank == 0) g_loop_seconds = secs;

@@ -220,23 +220,107 @@ class RegularGrid(Grid):
             raise KeyError("Number of equations must be the same as number of fields. Number of fields is ",
                            len(self.fields))
         self.eq = list(equations)
+        self.generic = False
+        self.axis_weights = None
+        try:
+            self._solve_fd_acoustic()
+        except NotImplementedError:
+            # any other PDE system: derive the update like the reference does and compile it at run time
+            self._solve_fd_generic()
+
+    def _solve_fd_acoustic(self):
+        """`d2u/dt2 = sum_d w_d d2u/dx_d2` of a single field: served by the fixed-function kernels."""
+        if len(self.fields) != 1:
+            raise NotImplementedError("fixed-function path: one field")
         field = self.fields[0]
         eq = self.eq[0]
         if not (isinstance(eq.lhs, DDerivative) and _same_field(eq.lhs.field, field) and eq.lhs.axis == 0
                 and eq.lhs.order == 2):
-            raise NotImplementedError("RegularGrid on B200 supports d2u/dt2 = sum_d w_d d2u/dx_d2 only")
+            raise NotImplementedError("fixed-function path: d2u/dt2 = sum_d w_d d2u/dx_d2 only")
         weights = [0] * self.dimension
         for d, c in self._linear_coefficients(eq).items():
             if not _same_field(d.field, field) or d.order != 2 or d.axis == 0:
-                raise NotImplementedError("RegularGrid on B200: unsupported term %s" % d)
+                raise NotImplementedError("fixed-function path: unsupported term %s" % d)
             weights[d.axis - 1] = weights[d.axis - 1] + c
         self.axis_weights = weights
         field.set_dt(eq.rhs)
+
+    def _solve_fd_generic(self):
+        """reference: regulargrid.py:230-270, verbatim in method: substitute every derivative symbol by its
+        finite-difference expression of the grid's accuracy, solve each equation for the field at the newest time level
+        with sympy, keep the symbolic kernel.  Lowered by `_build_params_generic` into CUDA source that the library
+        compiles with NVRTC (include/opesci_b200.h: OPESCI_KIND_REGULAR_GENERIC)."""
+        from sympy import solve
+        if self.dimension != 3:
+            raise NotImplementedError("B200 path: 3-D models only")
+        if len(self.time) != 3:
+            raise NotImplementedError("generic PDEs: three time levels (calc_derivatives(2), second order in time) -- "
+                                      "the reference's RegularGrid maps the kernel onto _t0, _t1, _t2 (regulargrid.py:592-599)")
+        t = self.t
+        index_new = [t + 1 + (self.order[0] // 2 - 1)] + self.index
+        simplify = max(self.order[1:]) <= 4
+        for field, eq in zip(self.fields, self.eq):
+            field.set_dt(eq.rhs)
+            for deriv in get_all_objects(eq, DDerivative):
+                eq = eq.subs(deriv, deriv.fd[deriv.max_accuracy])
+            sols = solve(eq, field[index_new], simplify=simplify)
+            if len(sols) != 1:
+                raise NotImplementedError("equation for %s cannot be solved for the newest time level" % field.label)
+            field.kernel = sols[0].subs({t: t - (self.order[0] // 2 - 1)})
+        self.generic = True
+
+    # ---- the reference's kernel transformations (regulargrid.py:329-342, 530-564, 601-604)
+    def transform_kernel(self, field):
+        kernel = field.kernel
+        if self.expand:
+            kernel = expand(kernel)
+        if self.eval_const:
+            self.create_const_dict()
+            kernel = kernel.subs(self.const_dict)
+        return kernel
+
+    def kernel_sympy(self, field):
+        tv = [Symbol(v.name) for v in self.time]
+        return self.transform_kernel(field).xreplace({self.t + 1: tv[2], self.t: tv[1], self.t - 1: tv[0]})
+
+    def second_initialisation_sympy(self, field):
+        """regulargrid.py:547-556: the `-F[t-1]` term of the kernel is replaced by 2*v*dt and the sum halved."""
+        v = symbols("v")
+        kernel = self.transform_kernel(field)
+        for arg in kernel.args:
+            if str(arg).startswith("-") and str(self.t - 1) in str(arg):
+                kernel = kernel.subs({arg: 0}, simultaneous=True)
+                kernel = 0.5 * (kernel + 2 * v * self.dt)      # `self.dt` is a Variable, like in the reference: prints `v*dt`
+        kernel = kernel.subs({self.t: Symbol(self.time[0].name)})
+        for idx in self.index:
+            kernel = kernel.subs(idx, Symbol('_' + idx.name))
+        return kernel
+
+    def generic_kernel_text(self):
+        """The assignments the reference's generator would emit: (time-loop body, second initialisation body)."""
+        tv = [Symbol(v.name) for v in self.time]
+        loop = [Symbol('_' + x.name) for x in self.index]
+        step = ['%s = %s;' % (ccode(f[[tv[2]] + self.index]), ccode(self.kernel_sympy(f))) for f in self.fields]
+        init2 = ['%s = %s;' % (ccode(f[[tv[1]] + loop]), ccode(self.second_initialisation_sympy(f))) for f in self.fields]
+        return step, init2
 
     def get_kernel_ai(self, fields=None):
         """(AI, AI_w, ADD, MUL, LOAD, STORE) of the expanded update as the reference counts it
         (regulargrid.py:293-327): one MUL per weighted neighbour, one ADD per extra term."""
         m = self.margin.value
+        if getattr(self, 'generic', False):
+            # one MUL per printed term with a literal, one ADD per extra term, all fields (regulargrid.py:293-327)
+            self.create_const_dict()
+            add = mul = 0
+            loads = set()
+            for f in self.fields:
+                args = self.transform_kernel(f).args
+                add += len(args) - 1
+                mul += sum(1 for a in args if len(a.args) > 1)
+                loads |= {str(i.base.label) for i in get_all_objects(self.transform_kernel(f), Indexed)}
+            word = 8 if self.double else 4
+            ai = float(add + mul) / (len(loads) + len(self.fields)) / word
+            return (ai, ai * (add + mul) / max(add, mul, 1) / 2.0, add, mul, len(loads), len(self.fields))
         nterms = 1 + sum(2 * m for w in self.axis_weights if w != 0) + 1
         add, mul, load, store = nterms - 1, nterms - 1 + 1, 1, 1
         word = 8 if self.double else 4
@@ -308,7 +392,78 @@ class RegularGrid(Grid):
         text = ccode(placeholder - field.sol.subs(self.t, tn))
         return text.replace(ccode(placeholder), '__F__')
 
+    def _generic_source(self):
+        """CUDA C++ for OPESCI_KIND_REGULAR_GENERIC: constants as the reference defines them at the top of
+        opesci_execute (regulargrid.py:391-406), arrays as pointer-to-array casts (:474-496), one thread per point of
+        the loops [m, dim-m)^3 (:566-590), the emitted assignments verbatim."""
+        m = self.margin.value
+        dims = [self.dim[d].value for d in range(3)]
+        pitch = (dims[2] + 31) // 32 * 32
+        rt = 'double' if self.double else 'float'
+        step, init2 = self.generic_kernel_text()
+        names = [str(f.label) for f in self.fields]
+        consts = []
+        for var in self.get_all_variables():
+            if var.constant and var.name not in ('dim1', 'dim2', 'dim3'):
+                consts.append('    const %s %s = %r;' % (var.type, var.name, var.value))
+        casts = ['    real_t (*%s)[%d][%d][%d] = (real_t (*)[%d][%d][%d]) p%d;' % (n, dims[0], dims[1], pitch, dims[0], dims[1], pitch, k)
+                 for k, n in enumerate(names)]
+        params = ', '.join('real_t *p%d' % k for k in range(len(names)))
+
+        def kernel(name, levels, x, y, z, body):
+            return '\n'.join([
+                'extern "C" __global__ void __launch_bounds__(256) %s(%s, %s)' % (name, params, ', '.join('int ' + l for l in levels)),
+                '{',
+                '    const int dim1 = %d, dim2 = %d, dim3 = %d;' % tuple(dims),
+                '\n'.join(consts),
+                '\n'.join(casts),
+                '    const int %s = %d + (int)(blockIdx.x * blockDim.x + threadIdx.x);' % (z, m),
+                '    const int %s = %d + (int)(blockIdx.y * blockDim.y + threadIdx.y);' % (y, m),
+                '    const int %s = %d + (int)blockIdx.z;' % (x, m),
+                '    if (%s >= dim3 - %d || %s >= dim2 - %d || %s >= dim1 - %d) return;' % (z, m, y, m, x, m),
+                '\n'.join('    ' + line for line in body),
+                '}', ''])
+        idx = [i.name for i in self.index]
+        tnames = [v.name for v in self.time]
+        src = ['// generated by opesci_fd_b200.RegularGrid (generic PDE path); expressions as the reference prints them',
+               'typedef %s real_t;' % rt,
+               kernel('opesci_generic_step', tnames, idx[0], idx[1], idx[2], step),
+               kernel('opesci_generic_init2', tnames[:2], '_' + idx[0], '_' + idx[1], '_' + idx[2], init2)]
+        return '\n'.join(src)
+
+    def _build_params_generic(self):
+        keep = []
+        m = self.margin.value
+        nf = len(self.fields)
+        if nf > abi.OPESCI_MAX_FIELDS:
+            raise NotImplementedError("at most %d fields" % abi.OPESCI_MAX_FIELDS)
+        p = self._common_params(abi.KIND_REGULAR_GENERIC, nf, len(self.time))
+        p.free_surface = abi.FS_NONE
+        source = self._generic_source().encode()
+        p.generic_source = source
+        keep.append(source)
+        self.generic_source = source.decode()
+        loop = [Symbol('_' + x.name) for x in self.index]
+        coords = self._coordinates([False] * 3)
+        ti = self.ntsteps.value % 2
+        tn = self.dt.value * self.ntsteps.value
+        dims = [self.dim[d].value for d in range(3)]
+        for k, field in enumerate(self.fields):
+            # level 0 := sol(t=0) over the WHOLE array with the integer loop indices as coordinates
+            # (regulargrid.py:498-528); L2 on [m,dim-m) against sol(ntsteps*dt) (regulargrid.py:650-700)
+            sol0 = field.sol.subs(self.t, 0)
+            for idx in self.index:
+                sol0 = sol0.subs(idx, Symbol('_' + idx.name))
+            fvars = self._solution_variables(coords)
+            fvars.field('__F__', cexpr.DOUBLE if self.double else cexpr.FLOAT)
+            self._field_spec(p, k, field, [0] * 3, dims, [m] * 3, [n - m for n in dims],
+                             ccode(sol0), self._solution_variables(None),
+                             self._residual_text(field, ti, tn, loop), fvars, keep)
+        return p, keep
+
     def build_params(self):
+        if getattr(self, 'generic', False):
+            return self._build_params_generic()
         if not getattr(self, 'axis_weights', None):
             raise RuntimeError("solve_fd() must be called before the model can be lowered")
         if self.order[0] != 2:

@@ -44,6 +44,12 @@ def make_grid(cfg, flags=None):
                             rho=cfg.get("rho", 1.0), vp=cfg.get("vp", 1.0), vs=cfg.get("vs", 0.5), verbose=False)
         if "faces" in cfg:   # free surfaces on a subset of the faces (the driver sets all six)
             g._free_surface = {tuple(f) for f in cfg["faces"]}
+    elif cfg["kind"] == "regular_generic":
+        # PDE systems outside the fixed-function kernels (tests/generic_pdes.py): NVRTC path
+        import generic_pdes
+        import opesci_fd_b200
+        g = generic_pdes.build(opesci_fd_b200, cfg["pde"], tuple(cfg["domain"]), tuple(cfg["grid_size"]), cfg["dt"],
+                               cfg["dt"] * cfg["steps"], order, double=cfg["double"])
     else:
         import simplewaveequation as drv
         g = drv.simplewave3d(tuple(cfg["domain"]), tuple(cfg["grid_size"]), cfg["dt"], cfg["dt"] * cfg["steps"],

@@ -43,7 +43,7 @@ def kernel_literals(cfg):
     body = src[src.index("_ti < ntsteps"):]
     out = {}
     for f in cfg["fields"]:
-        lvl = "_t2" if cfg["kind"] == "simplewave3d" else "_t1"
+        lvl = "_t2" if cfg["kind"] in ("simplewave3d", "regular_generic") else "_t1"
         m = re.search(r"^\s*%s\[%s\]\[x\]\[y\]\[z\] = (.*);$" % (f, lvl), body, re.M)
         terms = re.findall(r"(?:^|\s)([+-]?)\s*([0-9.]+(?:e[+-]?\d+)?)F\*", m.group(1))
         out[f] = [("-" if s == "-" else "") + lit for s, lit in terms]
@@ -89,12 +89,27 @@ def main():
         elif tags & {"default", "mid"}:
             vals, printed = run(cfg)
             norms[name] = dict(config={k: cfg[k] for k in ("kind", "so", "grid_size", "dt", "steps", "double",
-                                                           "domain", "dim", "fields")},
+                                                           "domain", "dim", "fields") + (("pde",) if "pde" in cfg else ())},
                                l2=vals, l2_printed=printed)
             if "rho" in cfg:
                 norms[name]["config"].update(rho=cfg["rho"], vp=cfg["vp"], vs=cfg["vs"])
             literals[name] = kernel_literals(cfg)
             print("norms", name, printed[:2])
+    # generic PDE systems: the assignments of the time loop and of the second initialisation, as emitted
+    gk_path = os.path.join(HERE, "generic_kernels.json")
+    gk = json.load(open(gk_path)) if os.path.exists(gk_path) else {}
+    for name, cfg in sorted(MAN.items()):
+        if cfg["kind"] != "regular_generic" or (only and not any(o in name for o in only)):
+            continue
+        lines = [l.strip() for l in open(os.path.join(ROOT, cfg["cpp"]))]
+        step = [l for l in lines if re.match(r"^\w+\[_t2\]\[x\]\[y\]\[z\] = ", l)]
+        init2 = []
+        for l in lines:
+            if re.match(r"^\w+\[_t1\]\[_x\]\[_y\]\[_z\] = ", l) and l not in init2:
+                init2.append(l)
+        gk[name] = dict(config={k: cfg[k] for k in ("kind", "pde", "so", "grid_size", "dt", "steps", "double", "domain", "dim", "fields")},
+                        step=step, init2=init2)
+    json.dump(gk, open(gk_path, "w"), indent=1, sort_keys=True)
     json.dump(hashes, open(os.path.join(HERE, "hashes.json"), "w"), indent=1, sort_keys=True)
     json.dump(norms, open(os.path.join(HERE, "norms.json"), "w"), indent=1, sort_keys=True)
     json.dump(literals, open(os.path.join(HERE, "literals.json"), "w"), indent=1, sort_keys=True)
