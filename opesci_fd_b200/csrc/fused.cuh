@@ -475,6 +475,26 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     const int zf_far_lane = ZF ? ((A.zf_side[1] && bx == A.zf_bx[1]) ? ((tz == A.zf_c[1] + 2) ? 0 : (tz + 1 == A.zf_c[1] + 2) ? 1 : -1) : -1) : -1;
     const bool zf_far = zf_far_lane >= 0 && ze + zf_far_lane < G.dim[2] && ye < G.dim[1];
     if (ZF && zf_far) zz_far = gT1[2][px + zf_far_lane];
+    // ZF: one z face per tile column (the host requires at least two tile columns).  Everything that does not change from
+    // plane to plane is worked out once: the face side of this column, the source columns of the mirrors (CTA-uniform)
+    // and, per thread, which of its two columns takes which part -- `zrole`, 4 bits per column:
+    //   1 face plane b (Levander recompute of Txx, Tyy; Tzz = 0)      2 Tzz mirror target b + dir
+    //   4 / 8 first / second shear mirror target
+    const int zside = (ZF && A.zf_side[1] && bx == A.zf_bx[1]) ? 1 : 0;
+    const bool zf_tile = ZF && A.zf_side[zside] && bx == A.zf_bx[zside];
+    const int zc = A.zf_c[zside], zdir = zside == 0 ? -1 : 1;
+    const int zs_zz = zc - zdir;
+    const int zd0 = zside == 0 ? zc - 1 : zc, zs0 = zside == 0 ? zc : zc - 1;
+    const int zd1 = zside == 0 ? zc - 2 : zc + 1, zs1 = zside == 0 ? zc + 1 : zc - 2;
+    unsigned zrole = 0;
+    if (ZF && zf_tile && zf_row) {
+#pragma unroll
+        for (int L = 0; L < 2; ++L) {
+            const int j = tz + L;
+            zrole |= (unsigned)((j == zc ? 1 : 0) | (j == zc + zdir ? 2 : 0) | (j == zd0 ? 4 : 0) | (j == zd1 ? 8 : 0)) << (4 * L);
+        }
+    }
+    const bool zrow_stores = ty >= M && ty < M + K::CY;
 #if OPESCI_T0_AHEAD == 2
     static_assert(RD % 2 == 0, "plane parity must survive the unrolled loop");
     if (xs_begin + 1 < xs_end) load_told(told_buf[1], px + sx);
@@ -691,25 +711,20 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                 // ---- z-face stress ghost loops of this plane, in registers (see the kernel's header comment).
                 // tn[L][k]: 0 Txx, 1 Tyy, 2 Tzz, 3 Txy, 4 Tyz, 5 Txz.  A warp is one tile row, so every source
                 // column lives in this warp: shuffles, executed by all lanes (warp-uniform branch).
-                if (zf_row && xs >= A.zf_xlo && xs < A.zf_xhi) {
-#pragma unroll
-                    for (int side = 0; side < 2; ++side) {
-                        if (!A.zf_side[side] || bx != A.zf_bx[side]) continue;    // CTA-uniform
-                        const int c = A.zf_c[side], dir = side == 0 ? -1 : 1;
-                        // Tzz[b + dir] = -Tzz[b - dir]; shear: low T[b-1] = -T[b], T[b-2] = -T[b+1]; high T[b'] = -T[b'-1],
-                        // T[b'+1] = -T[b'-2] (opesci/fields.py:355-381)
-                        const int szz = c - dir;
-                        const int dst0 = side == 0 ? c - 1 : c, src0 = side == 0 ? c : c - 1;
-                        const int dst1 = side == 0 ? c - 2 : c + 1, src1 = side == 0 ? c + 1 : c - 2;
-                        const T zz = __shfl_sync(0xffffffffu, (szz & 1) ? tn[1][2] : tn[0][2], szz >> 1);
-                        const T yz0 = __shfl_sync(0xffffffffu, (src0 & 1) ? tn[1][4] : tn[0][4], src0 >> 1);
-                        const T xz0 = __shfl_sync(0xffffffffu, (src0 & 1) ? tn[1][5] : tn[0][5], src0 >> 1);
-                        const T yz1 = __shfl_sync(0xffffffffu, (src1 & 1) ? tn[1][4] : tn[0][4], src1 >> 1);
-                        const T xz1 = __shfl_sync(0xffffffffu, (src1 & 1) ? tn[1][5] : tn[0][5], src1 >> 1);
+                if (zf_tile && zf_row && xs >= A.zf_xlo && xs < A.zf_xhi) {
+                    // Tzz[b + dir] = -Tzz[b - dir]; shear: low T[b-1] = -T[b], T[b-2] = -T[b+1]; high T[b'] = -T[b'-1],
+                    // T[b'+1] = -T[b'-2] (opesci/fields.py:355-381)
+                    const T zz = __shfl_sync(0xffffffffu, (zs_zz & 1) ? tn[1][2] : tn[0][2], zs_zz >> 1);
+                    const T yz0 = __shfl_sync(0xffffffffu, (zs0 & 1) ? tn[1][4] : tn[0][4], zs0 >> 1);
+                    const T xz0 = __shfl_sync(0xffffffffu, (zs0 & 1) ? tn[1][5] : tn[0][5], zs0 >> 1);
+                    const T yz1 = __shfl_sync(0xffffffffu, (zs1 & 1) ? tn[1][4] : tn[0][4], zs1 >> 1);
+                    const T xz1 = __shfl_sync(0xffffffffu, (zs1 & 1) ? tn[1][5] : tn[0][5], zs1 >> 1);
+                    if (zrole != 0) {      // the two or three lanes of the row that hold a face / ghost column
+                        const bool own = xs >= xa && xs < xb && zrow_stores;
 #pragma unroll
                         for (int L = 0; L < 2; ++L) {
-                            const int j = tz + L;
-                            if (j == c) {
+                            const unsigned r4 = (zrole >> (4 * L)) & 15u;
+                            if (r4 & 1u) {
                                 // Levander: T_ee[t1] = T_ee[t0] + (bwd window of U along x) + (bwd window of V along y), emitted
                                 // order +1, -1, -2, 0 per window, separate multiply and add (face_batch evaluates the same
                                 // term table the same way in either arithmetic mode)
@@ -729,26 +744,22 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                                 }
                                 tn[L][2] = (T)0;
                             }
-                            if (j == c + dir) tn[L][2] = -zz;
-                            if (j == dst0) { tn[L][4] = -yz0; tn[L][5] = -xz0; }
-                            if (j == dst1) { tn[L][4] = -yz1; tn[L][5] = -xz1; }
-                            // Tzz two columns beyond the high face (z = dim3-1) is written by no loop: the W update of the
-                            // face plane reads it, so the window must hold what the array holds
-                            if (side == 1 && zf_far && L == zf_far_lane) tn[L][2] = zz_far;
-                        }
-                        // the ghost columns this plane's loops wrote (owned planes only; the interior columns go out below)
-                        if (xs >= xa && xs < xb && ty >= M && ty < M + K::CY) {
-#pragma unroll
-                            for (int L = 0; L < 2; ++L) {
-                                const int j = tz + L;
-                                if (j == c + dir) gstore(gT1[2] + px + L, tn[L][2]);
-                                if ((side == 0 && (j == dst0 || j == dst1)) || (side == 1 && j == dst1)) {
+                            if (r4 & 2u) tn[L][2] = -zz;
+                            if (r4 & 4u) { tn[L][4] = -yz0; tn[L][5] = -xz0; }
+                            if (r4 & 8u) { tn[L][4] = -yz1; tn[L][5] = -xz1; }
+                            // the ghost columns this plane's loops wrote (owned planes only; the interior columns go out below)
+                            if (own) {
+                                if (r4 & 2u) gstore(gT1[2] + px + L, tn[L][2]);
+                                if ((r4 & 8u) || (zside == 0 && (r4 & 4u))) {
                                     gstore(gT1[4] + px + L, tn[L][4]);
                                     gstore(gT1[5] + px + L, tn[L][5]);
                                 }
                             }
                         }
                     }
+                    // Tzz two columns beyond the high face (z = dim3-1) is written by no loop: the W update of the face plane
+                    // reads it, so the window must hold what the array holds
+                    if (zf_far) { if (zf_far_lane == 0) tn[0][2] = zz_far; else tn[1][2] = zz_far; }
                 }
             }
             // ---- store the new stresses (owned tile, owned planes), prefetch next T[t0]

@@ -1280,7 +1280,8 @@ int setup_fused(Run &R)
     if (m == 2 && p.free_surface == 1 && !p.hetero && R.zstrip == 0 && !(p.flags & OPESCI_NO_ZFOLD) && !getenv("OPESCI_NO_ZFOLD") &&
         ((fs_mask >> 4) & 3) == 3) {   // both z faces carry the free surface
         const int c_hi = (p.dim[2] - m - 1) - (nztiles - 1) * CZ;
-        if (c_hi >= 2 * m && c_hi + 2 <= FusedCfg<2>::EZ - 1 && p.dim[1] >= 4 * m + 6 && M.G.dim[0] >= 4 * m + 6) {
+        // (at least two tile columns: the z-edge kernel handles one face per column)
+        if (nztiles >= 2 && c_hi >= 2 * m && c_hi + 2 <= FusedCfg<2>::EZ - 1 && p.dim[1] >= 4 * m + 6 && M.G.dim[0] >= 4 * m + 6) {
             int prio_lo = 0, prio_hi = 0;
             CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
             // higher priority: the few z-edge CTAs are scheduled as soon as they are ready instead of behind every
