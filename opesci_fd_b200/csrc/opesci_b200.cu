@@ -605,6 +605,26 @@ struct Stepper {
                     const int nbz = (int)((Md.G.s[1] / 4 + 31) / 32), nby = (ny + 7) / 8;
                     int nchunks = (8 * sm_count() + nbz * nby - 1) / (nbz * nby);   // >= 8 blocks per SM in flight
                     if (nchunks < 1) nchunks = 1;
+                    {
+                        // whole waves: the step is a fraction of a millisecond at 512^3, so a last wave that is nearly empty
+                        // costs a visible share.  Among the chunk counts up to 4x the minimum pick the one with the best
+                        // (wave fill) x (1 - window warm-up share).
+                        static int occ = 0;
+                        if (!occ && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, acoustic_march<SO, ARITH>, 256, 0) != cudaSuccess) occ = 4;
+                        const double cap = (double)(occ > 0 ? occ : 4) * sm_count();
+                        double best = -1.0;
+                        int best_nc = nchunks;
+                        for (int nc = nchunks; nc <= 4 * nchunks + 4; ++nc) {
+                            const int len = (nx + nc - 1) / nc;
+                            if (len < 8 * Md.m) break;
+                            const double blocks = (double)nbz * nby * ((nx + len - 1) / len);
+                            const double waves = blocks / cap;
+                            const double eff = waves / (double)((long long)(waves + 0.999999)) * len / (len + 2.0 * Md.m);
+                            if (eff > best) { best = eff; best_nc = nc; }
+                        }
+                        static const char *force = getenv("OPESCI_AC_CHUNKS");
+                        nchunks = force ? atoi(force) : best_nc;
+                    }
                     if (nchunks > nx / (4 * Md.m) && nx / (4 * Md.m) >= 1) nchunks = nx / (4 * Md.m);
                     const int xchunk = (nx + nchunks - 1) / nchunks;
                     acoustic_march<SO, ARITH><<<dim3(nbz, nby, (nx + xchunk - 1) / xchunk), 256, 0, st>>>(ptrs(), Md.G, Md.ac, tprev, tr, tw, xchunk);
