@@ -493,7 +493,7 @@ def main():
         level_bytes = float(esz) * params.dim[1] * params.dim[2] * (params.dim[0] / world + (0 if world == 1 else 16))
         result_gb = params.nfields * nlev * level_bytes / 1e9
         # every rank copies all level arrays of its slab back into pinned host memory when the host has room for them
-        host_ok = mem_available_gb() > 1.25 * result_gb * min(world, 8)
+        host_ok = mem_available_gb() > 1.4 * result_gb * min(world, 8)     # (never drive the box near its memory limit)
         if world > 1:
             t = torch.tensor([1 if host_ok else 0], device="cuda", dtype=torch.int64)
             dist.all_reduce(t, op=dist.ReduceOp.MIN)

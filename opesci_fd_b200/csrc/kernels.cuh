@@ -249,8 +249,11 @@ acoustic_interior(FieldPtrs F, GridGeom G, AcousticCoefs C, int tprev, int tr, i
 // (one float4), marches along x with the 2M+1 planes of its own column in registers and reads the 2M
 // y-neighbours of the centre plane as float4 (L1 hits: they are the centre rows of neighbouring
 // threads).  12 B/point of compulsory traffic: read u[t1], read u[t0], write u[t2].
+#ifndef OPESCI_AC_MINB
+#define OPESCI_AC_MINB 4   /* resident blocks per SM the register allocation leaves room for (so <= 4) */
+#endif
 template <int SO, int ARITH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, SO <= 4 ? OPESCI_AC_MINB : 1)
 acoustic_march(FieldPtrs F, GridGeom G, AcousticCoefs C, int tprev, int tr, int tw, int xchunk)
 {
     constexpr int M = SO / 2;
@@ -542,53 +545,73 @@ struct VelZFaceArgs {
 template <typename T>
 __global__ void __launch_bounds__(256) vel_zface_lev(FieldPtrs F, GridGeom G, long long lvl, VelZFaceArgs A)
 {
-    const int y = A.y0 + blockIdx.x * 32 + (int)(threadIdx.x & 31);
-    const int x = A.x0 + blockIdx.y * 8 + (int)(threadIdx.x >> 5);
+    // A block owns TX x TY column ends of one z face.  Everything it reads lies in three consecutive z cells of the
+    // columns of its tile plus a one-column rim: z = 1..3 on the low face, dim-4..dim-2 on the high face -- one 32-byte
+    // sector per column and field.  The sectors are staged in shared memory first (each fetched once per block; through L1
+    // every 12 useful bytes would hold a 128-byte line and the re-reads by neighbouring threads missed: ncu showed 1.45 GB
+    // of DRAM reads for 0.2 GB of sectors), then every thread evaluates its expressions from there.
+    constexpr int TX = 8, TY = 32, RX = TX + 2, RY = TY + 2;
+    __shared__ T sm[3][RX * RY][3];
     const int side = blockIdx.z;
-    if (x >= A.x1 || y >= A.y1) return;
-    T *U = (T *)F.f[F_U] + lvl, *V = (T *)F.f[F_V] + lvl, *W = (T *)F.f[F_W] + lvl;
-    const long long sx = G.s[0], sy = G.s[1];
     const int m = A.m;
-    const T sg = side == 0 ? (T)1 : (T)-1;
+    const int xb = A.x0 + blockIdx.y * TX, yb = A.y0 + blockIdx.x * TY;     // first column of the tile
+    const long long sx = G.s[0], sy = G.s[1];
     const int nw = side == 0 ? m - 1 : A.dimz - m - 1;          // W ghost plane
-    const int zp = side == 0 ? nw + 1 : nw;                     // plane of the tangential differences
-    const int zs = side == 0 ? nw + 1 : nw - 1;                 // W[n +- 1]
+    const int nu = side == 0 ? m - 1 : A.dimz - m;              // U, V ghost plane
+    const int z0 = side == 0 ? m - 1 : A.dimz - m - 2;          // staged cells: z0, z0+1, z0+2
+    T *base[3] = {(T *)F.f[F_U] + lvl, (T *)F.f[F_V] + lvl, (T *)F.f[F_W] + lvl};
+    for (int i = threadIdx.x; i < 3 * RX * RY; i += 256) {
+        const int f = i / (RX * RY), r = i % (RX * RY);
+        const int x = xb - 1 + r / RY, y = yb - 1 + r % RY;
+        T v0 = 0, v1 = 0, v2 = 0;
+        if (x >= 0 && x < G.dim[0] && y >= 0 && y < G.dim[1]) {
+            const T *p = base[f] + (long long)x * sx + (long long)y * sy + z0;
+            v0 = p[0]; v1 = p[1]; v2 = p[2];
+        }
+        sm[f][r][0] = v0; sm[f][r][1] = v1; sm[f][r][2] = v2;
+    }
+    __syncthreads();
+    const int ly = (int)(threadIdx.x & 31), lx = (int)(threadIdx.x >> 5);
+    const int x = xb + lx, y = yb + ly;
+    if (x >= A.x1 || y >= A.y1) return;
+    const T sg = side == 0 ? (T)1 : (T)-1;
+    const int kp = (side == 0 ? nw + 1 : nw) - z0;               // plane of the tangential differences, as staged index
+    const int ks = (side == 0 ? nw + 1 : nw - 1) - z0;           // W[n +- 1]
+    const int kw = nw - z0;                                      // the W ghost cell itself
     const T c0 = (T)(-sg * A.cn[0]), c0p = (T)(sg * A.cn[0]), c1 = (T)(-sg * A.cn[1]), c1p = (T)(sg * A.cn[1]);
-    auto wghost = [&](int xx, int yy) -> T {
-        const long long q = (long long)xx * sx + (long long)yy * sy;
-        T acc = mul_rn<T>(c0, U[q - sx + zp]);
-        acc = add_rn<T>(acc, mul_rn<T>(c0p, U[q + zp]));
-        acc = add_rn<T>(acc, mul_rn<T>(c1, V[q - sy + zp]));
-        acc = add_rn<T>(acc, mul_rn<T>(c1p, V[q + zp]));
-        acc = add_rn<T>(acc, W[q + zs]);
+    auto at = [&](int f, int dx, int dy, int k) -> T { return sm[f][(lx + 1 + dx) * RY + (ly + 1 + dy)][k]; };
+    // the value the W loop stores at column (x+dx, y+dy): term order of build_levander (opesci/fields.py:208-242)
+    auto wghost = [&](int dx, int dy) -> T {
+        T acc = mul_rn<T>(c0, at(0, dx - 1, dy, kp));
+        acc = add_rn<T>(acc, mul_rn<T>(c0p, at(0, dx, dy, kp)));
+        acc = add_rn<T>(acc, mul_rn<T>(c1, at(1, dx, dy - 1, kp)));
+        acc = add_rn<T>(acc, mul_rn<T>(c1p, at(1, dx, dy, kp)));
+        acc = add_rn<T>(acc, at(2, dx, dy, ks));
         return acc;
     };
     auto in_range = [&](int xx, int yy) { return xx >= A.x0 && xx < A.x1 && yy >= A.y0 && yy < A.y1; };
-    const long long q = (long long)x * sx + (long long)y * sy;
-    const T wg = wghost(x, y);
+    const T wg = wghost(0, 0);
     // W ghosts of the +x / +y neighbours: what their own threads store, or -- outside the W loop's range -- what the array holds
-    const T wg_xp = in_range(x + 1, y) ? wghost(x + 1, y) : W[q + sx + nw];
-    const T wg_yp = in_range(x, y + 1) ? wghost(x, y + 1) : W[q + sy + nw];
-    const int nu = side == 0 ? m - 1 : A.dimz - m;               // U, V ghost plane
-    const int pl1 = side == 0 ? 1 : -2, sf0 = side == 0 ? 1 : -1, sf1 = side == 0 ? 2 : -2;
+    const T wg_xp = in_range(x + 1, y) ? wghost(1, 0) : at(2, 1, 0, kw);
+    const T wg_yp = in_range(x, y + 1) ? wghost(0, 1) : at(2, 0, 1, kw);
+    const int k1 = nu + (side == 0 ? 1 : -2) - z0, kf0 = nu + (side == 0 ? 1 : -1) - z0, kf1 = nu + (side == 0 ? 2 : -2) - z0;
     const T two = (T)2.0f;
     T out[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-        const T *Ve = e == 0 ? U : V;
-        const long long se = e == 0 ? sx : sy;
         const T g = (T)(sg * A.gt[e]), gn = (T)(-sg * A.gt[e]);
-        T acc = mul_rn<T>(two, Ve[q + nu + sf0]);
-        acc = add_rn<T>(acc, -Ve[q + nu + sf1]);
+        T acc = mul_rn<T>(two, at(e, 0, 0, kf0));
+        acc = add_rn<T>(acc, -at(e, 0, 0, kf1));
         acc = add_rn<T>(acc, mul_rn<T>(g, e == 0 ? wg_xp : wg_yp));
-        acc = add_rn<T>(acc, mul_rn<T>(gn, W[q + se + nu + pl1]));
+        acc = add_rn<T>(acc, mul_rn<T>(gn, e == 0 ? at(2, 1, 0, k1) : at(2, 0, 1, k1)));
         acc = add_rn<T>(acc, mul_rn<T>(gn, wg));
-        acc = add_rn<T>(acc, mul_rn<T>(g, W[q + nu + pl1]));
+        acc = add_rn<T>(acc, mul_rn<T>(g, at(2, 0, 0, k1)));
         out[e] = acc;
     }
-    W[q + nw] = wg;
-    U[q + nu] = out[0];
-    V[q + nu] = out[1];
+    const long long q = (long long)x * sx + (long long)y * sy;
+    base[2][q + nw] = wg;
+    base[0][q + nu] = out[0];
+    base[1][q + nu] = out[1];
 }
 
 // ------------------------------------------------------------------ point source + receivers

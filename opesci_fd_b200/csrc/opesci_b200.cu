@@ -606,24 +606,15 @@ struct Stepper {
                     int nchunks = (8 * sm_count() + nbz * nby - 1) / (nbz * nby);   // >= 8 blocks per SM in flight
                     if (nchunks < 1) nchunks = 1;
                     {
-                        // whole waves: the step is a fraction of a millisecond at 512^3, so a last wave that is nearly empty
-                        // costs a visible share.  Among the chunk counts up to 4x the minimum pick the one with the best
-                        // (wave fill) x (1 - window warm-up share).
-                        static int occ = 0;
-                        if (!occ && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, acoustic_march<SO, ARITH>, 256, 0) != cudaSuccess) occ = 4;
-                        const double cap = (double)(occ > 0 ? occ : 4) * sm_count();
-                        double best = -1.0;
-                        int best_nc = nchunks;
-                        for (int nc = nchunks; nc <= 4 * nchunks + 4; ++nc) {
-                            const int len = (nx + nc - 1) / nc;
-                            if (len < 8 * Md.m) break;
-                            const double blocks = (double)nbz * nby * ((nx + len - 1) / len);
-                            const double waves = blocks / cap;
-                            const double eff = waves / (double)((long long)(waves + 0.999999)) * len / (len + 2.0 * Md.m);
-                            if (eff > best) { best = eff; best_nc = nc; }
-                        }
+                        // Short chunks win (measured on B200 at 512^3, so=4, fast / reference arithmetic: 4 chunks 318 / 327 Gpts/s,
+                        // 9: 336 / 381, 16: 353 / 383, 32: 351 / 385) although each chunk re-reads 2m planes of ONE of the three
+                        // streams: the step is a fraction of a millisecond, and many short blocks keep the machine evenly filled
+                        // to the end.  Chunks of about 32 planes, never shorter than 8m.
+                        const int want = 32 > 8 * Md.m ? 32 : 8 * Md.m;
+                        const int nc = nx / want;
+                        if (nc > nchunks) nchunks = nc;
                         static const char *force = getenv("OPESCI_AC_CHUNKS");
-                        nchunks = force ? atoi(force) : best_nc;
+                        if (force) nchunks = atoi(force);
                     }
                     if (nchunks > nx / (4 * Md.m) && nx / (4 * Md.m) >= 1) nchunks = nx / (4 * Md.m);
                     const int xchunk = (nx + nchunks - 1) / nchunks;
