@@ -130,6 +130,7 @@ enum {
     OPESCI_FORCE_TILED = 1 << 11,
     OPESCI_NO_ZFOLD = 1 << 13,          /* diagnostic: keep the z-face stress ghost loops and the z slabs of the velocity shell in
                                          * the separate face / shell kernels instead of the z-edge tiles of the fused kernel */
+    OPESCI_NO_PAIR = 1 << 14,           /* diagnostic: interior fused launch as single CTAs instead of 2-CTA clusters stacked in y */
     OPESCI_L2_REFERENCE = 1 << 12,      /* opesci_convergence accumulates like the reference: serially, in real_t, in loop
                                          * order (staggeredgrid.py:916,935) -- reproduces its printed digits; a serial
                                          * chain by definition (seconds at 256^3), single rank only.  Default: double tree */       /* TMA-tiled two-pass kernels also where the fused kernel applies (diagnostic) */

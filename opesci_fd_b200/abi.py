@@ -34,6 +34,7 @@ OVERLAP = 1 << 10
 FORCE_TILED = 1 << 11
 L2_REFERENCE = 1 << 12
 NO_ZFOLD = 1 << 13
+NO_PAIR = 1 << 14
 
 FS_NONE, FS_LEVANDER, FS_ROBERTSSON = 0, 1, 2
 

@@ -168,6 +168,12 @@ template <int M> struct FusedCfg {
     static constexpr int STILE = EZ * EY * 4;
     static constexpr int SMEM = 3 * RD * VTILE + 5 * SR * STILE + 3 * RD * 8 + 128;
     static constexpr int THREADS = EZ / 2 * EY;             // two z-adjacent points per thread
+    // ---- PAIR kernels: two CTAs stacked in y form a thread-block cluster.  Each stores EY - M rows (the recomputed halo
+    // rows exist only on the outer side of the pair); the M stress rows one CTA needs from the other for its velocity
+    // y-windows arrive through distributed shared memory, so a ring slot holds EY + M rows.
+    static constexpr int PCY = EY - M;                      // rows stored per CTA of a pair
+    static constexpr int PSTILE = EZ * (EY + M) * 4;
+    static constexpr int PSMEM = 3 * RD * VTILE + 5 * SR * PSTILE + 3 * RD * 8 + 128 + 2 * SR * 8;
 };
 
 struct FusedArgs {
@@ -285,7 +291,14 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *tmap, const void
 // there no x-/y-face loop writes any cell these operations read or write, so the result is cell for cell what the
 // separate face kernels produce; the thin remainder next to the x / y faces stays with them (Stepper::stress_bc).
 // A separate instantiation, so the interior tiles keep their register budget.
-template <int SO, int ARITH, bool HET = false, bool ZF = false>
+// PAIR = true: the interior launch as 2-CTA clusters stacked in y (see FusedCfg::PCY).  After a CTA has published the
+// stresses of a plane it pushes the M rows next to its partner -- Txy, Tyy, Tyz, the fields with y-windows -- into the
+// partner's ring slot with st.async (distributed shared memory; the bytes count on the partner's `full` mbarrier of that
+// slot), and the partner waits for them only M planes later, when its velocity update reads the slot.  A slot is
+// refilled only after the partner has reported -- one remote arrival on this CTA's `empty` mbarrier -- that it has read the
+// plane that lived there.  Same arithmetic on the same operands as the single-CTA tiles: bit-identical results; what
+// changes is that 2M fewer halo rows per pair are loaded, recomputed and re-fetched.
+template <int SO, int ARITH, bool HET = false, bool ZF = false, bool PAIR = false>
 __global__ void __launch_bounds__(FusedCfg<SO / 2>::THREADS, OPESCI_FUSED_MINB)
 fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
            const __grid_constant__ CUtensorMap tmW, const FusedArgs A
@@ -299,13 +312,15 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     typedef float T;
     constexpr int RD = K::RD;
     constexpr int VT = K::VTILE / 4;      // floats per velocity tile
-    constexpr int ST = K::STILE / 4;      // floats per stress tile
+    constexpr int ST = (PAIR ? K::PSTILE : K::STILE) / 4;      // floats per stress tile
+    static_assert(!PAIR || (!ZF && !HET), "pairs: interior launch of the homogeneous model only");
     // dynamic shared memory (no static __shared__ in this kernel, so the window starts 1024-B
     // aligned): [3][RD] velocity tiles | [5][SR] stress tiles | mbarriers
     extern __shared__ __align__(1024) unsigned char smem[];
     const T *vring = reinterpret_cast<const T *>(smem);
     T *sring = reinterpret_cast<T *>(smem + (size_t)3 * RD * K::VTILE);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)3 * RD * K::VTILE + (size_t)5 * K::SR * K::STILE);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)3 * RD * K::VTILE + (size_t)5 * K::SR * (PAIR ? K::PSTILE : K::STILE));
+    uint64_t *pfull = bars + 3 * RD + 1, *pempty = pfull + K::SR;     // PAIR: halo rows arrived / slot read by the partner
 
 #ifndef OPESCI_SPLIT_BARRIER
 #define OPESCI_SPLIT_BARRIER 0
@@ -330,7 +345,14 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     if (ZF) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int bx = ZF ? A.bxs[blockIdx.x] : (int)blockIdx.x + A.bx0;       // tile column
     const int tz = 2 * (tid % (K::EZ / 2)), ty = tid / (K::EZ / 2);          // lane 0 sits at tz, lane 1 at tz+1
-    const int ye = blockIdx.y * K::CY + ty, ze = bx * K::CZ + tz - K::ZS;   // global coords of lane 0 (ze < 0: outside)
+    uint32_t prank = 0;       // PAIR: 0 = upper CTA of the pair (smaller y), 1 = lower
+    if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(prank));
+    // global y of thread row 0: tiles advance by CY rows; a pair advances by 2 PCY rows and its lower CTA starts EY rows down
+    const int tile_y0 = PAIR ? (int)(blockIdx.y >> 1) * (2 * K::PCY) + (int)prank * K::EY : (int)blockIdx.y * K::CY;
+    const int row_first = PAIR ? (prank == 0 ? M : 0) : M;          // first stored thread row
+    const int row_count = PAIR ? K::PCY : K::CY;                    // stored rows
+    const int ring_row = PAIR ? (prank == 0 ? 0 : M) : 0;           // slot row of thread row 0 (the lower CTA keeps M rows above)
+    const int ye = tile_y0 + ty, ze = bx * K::CZ + tz - K::ZS;   // global coords of lane 0 (ze < 0: outside)
     const int chunk = blockIdx.z + A.chunk0;
     const int xa = A.xs[chunk];
     const int xb = A.xs[chunk + 1];
@@ -339,7 +361,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     // x loop unrolled RD times every slot index below is a compile-time constant
     const int pbaseU = xs_begin - M, pbaseVW = xs_begin - M + 1;
     const int lastU = xs_end + M - 2, lastVW = xs_end + M - 1;
-    const int c0 = bx * K::CZ - K::OFFZ, c1 = blockIdx.y * K::CY - M;   // TMA box origin (may be negative)
+    const int c0 = bx * K::CZ - K::OFFZ, c1 = tile_y0 - M;   // TMA box origin (may be negative)
     const int lvl0 = A.t0 * G.dim[0];
     constexpr uint32_t TILE_BYTES = K::VZ * K::VY * 4;
 
@@ -348,10 +370,20 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 #if OPESCI_SPLIT_BARRIER
         mbar_init(&bars[3 * RD], K::THREADS / 32);   // step barrier: one arrival per warp and plane
 #endif
+        if (PAIR)
+            for (int i = 0; i < K::SR; ++i) { mbar_init(&pfull[i], 1); mbar_init(&pempty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
+    if (PAIR) {
+        // the partner's barriers exist before anything is pushed to it
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    // PAIR: rows this CTA pushes to its partner (the M stored rows next to it) and where they land in the partner's slot
+    const bool push_row = PAIR && (prank == 0 ? ty >= K::EY - M : ty < M);
+    const int push_dst_row = prank == 0 ? ty - (K::EY - M) : ty + K::EY;   // partner's slot row (its ring_row included)
     if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < RD; ++k) {
@@ -373,7 +405,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 #pragma unroll
     for (int L = 0; L < 2; ++L) {
         const int z = ze + L, t = tz + L;
-        const bool core = ty >= M && ty < M + K::CY && t >= M && t < M + K::CZ;
+        const bool core = ty >= row_first && ty < row_first + row_count && t >= M && t < M + K::CZ;
         inb[L] = ye < G.dim[1] && z >= 0 && z < G.dim[2];
         st_yz[L] = core && ye >= M && ye < G.dim[1] - M && z >= M && z < G.dim[2] - M;
         // velocities: deep interior; the z-edge variant also owns the z slabs of the shell (whole interior z range)
@@ -392,7 +424,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     // CTA-uniform: tiles whose whole 64 x 12 store box lies inside the interior (not the first tile column, whose halo
     // columns are ghost cells; not a ragged last column / row)
     const bool tma_st = OPESCI_TMA_STORE && !OPESCI_SPLIT_BARRIER && !ZF && bx > 0 &&
-                        bx * K::CZ - K::ZS + K::EZ <= G.dim[2] - M && (int)blockIdx.y * K::CY + M + K::CY <= G.dim[1] - M;
+                        bx * K::CZ - K::ZS + K::EZ <= G.dim[2] - M && tile_y0 + row_first + row_count <= G.dim[1] - M;
     const int xv_lo = max(xa, 2 * M + 1), xv_hi = min(xb, G.dim[0] - 2 * M - 1);
     const long long pyz = (long long)ye * G.s[1] + ze;
     const long long lv0 = (long long)A.t0 * G.level, lv1 = (long long)A.t1 * G.level;
@@ -420,7 +452,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     T vself[2] = {0, 0}, wself[2] = {0, 0};   // V,W[t0] at plane xs-M (saved one iteration earlier)
     const int lo = (ty + M) * K::VZ + tz + K::OFFZ - K::ZS;   // lane 0's element inside a velocity tile (even => 8-B aligned)
     const T *vlo = vring + lo;
-    T *slo = sring + ty * K::EZ + tz;
+    T *slo = sring + (ty + ring_row) * K::EZ + tz;
 
 #ifndef OPESCI_T0_BAND_POLICY
 #define OPESCI_T0_BAND_POLICY 0
@@ -812,6 +844,26 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                 *reinterpret_cast<float2 *>(s + 3 * K::SR * ST) = make_float2(tn[0][4], tn[1][4]);   // Tyz
                 *reinterpret_cast<float2 *>(s + 4 * K::SR * ST) = make_float2(tn[0][2], tn[1][2]);   // Tzz
             }
+            if constexpr (PAIR) {
+                if (push_row) {
+                    const int slot = xs & (K::SR - 1);
+                    // the partner has read the plane that lived in this slot (SR planes ago)?
+                    if (xs - K::SR >= xs_begin) mbar_wait(&pempty[slot], (uint32_t)(((xs - K::SR - xs_begin) / K::SR) & 1));
+                    // Txy, Tyy, Tyz of this row -> same columns of the partner's slot row; 8 bytes each, counted on its `full` barrier
+                    const uint32_t dst0 = smem_u32(sring + slot * ST + push_dst_row * K::EZ + tz);
+                    uint32_t rdst, rbar;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(dst0), "r"(prank ^ 1u));
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(&pfull[slot])), "r"(prank ^ 1u));
+                    const int kf[3] = {0, 2, 3};      // ring order: Txy, Txz, Tyy, Tyz, Tzz
+                    const int kt[3] = {3, 1, 4};      // tn index of Txy, Tyy, Tyz
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(
+                                         rdst + (uint32_t)(kf[i] * K::SR * ST * 4)),
+                                     "r"(__float_as_uint(tn[0][kt[i]])), "r"(__float_as_uint(tn[1][kt[i]])), "r"(rbar)
+                                     : "memory");
+                }
+            }
             T bet[2][3];   // heterogeneous mode: beta1, beta2, beta3 of the two cells (plane xv = xs - M), issued before the barrier
             if (HET) {
                 const bool vel_here = (vf_yz[0] || vf_yz[1]) && xs - M >= xv_lo && xs - M < xv_hi;
@@ -840,12 +892,25 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             }
 #endif
             __syncthreads();
+            if constexpr (PAIR) {
+                if (tid == 0) {
+                    // this plane's halo rows: 3 fields x M rows x EZ columns from the partner
+                    mbar_arrive_expect_tx(&pfull[xs & (K::SR - 1)], 3u * M * K::EZ * 4u);
+                    // every warp is past the velocity update of the previous iteration (plane xs-1-M): its slot may be refilled
+                    const int done = xs - 1 - M;
+                    if (done >= xs_begin) {
+                        uint32_t rbar;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(&pempty[done & (K::SR - 1)])), "r"(prank ^ 1u));
+                        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+                    }
+                }
+            }
 #if OPESCI_TMA_STORE
             if (tma_st && tid == 0 && xs >= xa && xs < xb) {
-                const T *s0 = sring + (xs & (K::SR - 1)) * ST + M * K::EZ;      // first core row of the slot
+                const T *s0 = sring + (xs & (K::SR - 1)) * ST + (row_first + ring_row) * K::EZ;      // first stored row of the slot
 #pragma unroll
                 for (int k = 0; k < 5; ++k)
-                    tma_store_3d(&SMAPS.m[k], s0 + k * K::SR * ST, bx * K::CZ - K::ZS, (int)blockIdx.y * K::CY + M,
+                    tma_store_3d(&SMAPS.m[k], s0 + k * K::SR * ST, bx * K::CZ - K::ZS, tile_y0 + row_first,
                                  A.t1 * G.dim[0] + xs);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -875,6 +940,10 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 #endif
             // ---- velocities of plane xv = xs - M from the new stresses xv-M .. xv+M
             const int xv = xs - M;
+            if constexpr (PAIR) {
+                // the partner's rows of plane xv (pushed M planes ago) are in the slot
+                if (xv >= xs_begin) mbar_wait(&pfull[xv & (K::SR - 1)], (uint32_t)(((xv - xs_begin) / K::SR) & 1));
+            }
             if ((vf_yz[0] || vf_yz[1]) && xv >= xv_lo && xv < xv_hi) {
                 const T *s = slo + (xv & (K::SR - 1)) * ST;
                 const T *sxy = s, *sxz = s + 1 * K::SR * ST, *syy = s + 2 * K::SR * ST, *syz = s + 3 * K::SR * ST,
@@ -976,6 +1045,11 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 #if OPESCI_TMA_STORE
     if (tma_st && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #endif
+    if (PAIR) {
+        // neither CTA leaves while the other may still push into it or signal it
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     // the kernels after this one read what the z-edge grid wrote: this grid completes only after that one has
     // (no-op when the launch has no programmatic dependency)
     if (!ZF) asm volatile("griddepcontrol.wait;" ::: "memory");

@@ -194,6 +194,8 @@ struct Run {
     int zstrip = 0;                 // > 0: the fused kernel covers z < zstrip only; the thin strip [zstrip, dim-m) is done per point
     int mid0 = 0, mid1 = 0;         // slabs: chunks [mid0, mid1) read no halo plane (they overlap the halo exchange)
     opesci_generic::Module gen;     // OPESCI_KIND_REGULAR_GENERIC: the NVRTC-compiled kernels of this model
+    bool pair = false;              // interior fused launch as 2-CTA clusters stacked in y (fused.cuh, PAIR)
+    StoreMaps smaps_pair;           // TMA store boxes of FusedCfg::PCY rows
     // z-fold (fused.cuh, ZF kernels): the z-face stress ghost loops and the z slabs of the velocity shell are done by the
     // z-edge tiles of the fused kernel, launched beside the interior tiles on a second stream
     bool zfold = false;
@@ -988,6 +990,20 @@ struct Stepper {
 #endif
 #if OPESCI_TMA_STORE
             if (Md.p.hetero) fused_step<SO, ARITH, true><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A, R.smaps);
+            else if (SO == 4 && R.pair) {
+                if constexpr (SO == 4) {
+                    // 2-CTA clusters stacked in y: a pair stores 2 * PCY rows
+                    const int npairs = (Md.G.dim[1] - 2 * M + 2 * K::PCY - 1) / (2 * K::PCY);
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(grid.x, 2 * npairs, grid.z); cfg.blockDim = dim3(K::THREADS); cfg.dynamicSmemBytes = K::PSMEM; cfg.stream = st;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    cudaError_t e = cudaLaunchKernelEx(&cfg, fused_step<SO, ARITH, false, false, true>, R.tmap[0], R.tmap[1], R.tmap[2], A, R.smaps_pair);
+                    if (e != cudaSuccess && err == cudaSuccess) err = e;
+                }
+            }
             else if (R.zfold && zf_pdl) {
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = grid; cfg.blockDim = dim3(K::THREADS); cfg.dynamicSmemBytes = K::SMEM; cfg.stream = st;
@@ -1308,6 +1324,25 @@ int setup_fused(Run &R)
             R.zfold = true;
             R.zf_nzt = nztiles;
         }
+    }
+    // ---- pairs: the interior launch of the z-fold configuration as 2-CTA clusters stacked in y (fused.cuh, PAIR)
+    R.pair = false;
+    if (R.zfold && !(p.flags & OPESCI_NO_PAIR) && !getenv("OPESCI_NO_PAIR") && nztiles >= 3) {
+        const int ring_field[5] = {F_TXY, F_TXZ, F_TYY, F_TYZ, F_TZZ};
+        bool ok = true;
+        for (int k = 0; k < 5 && ok; ++k) {
+            cuuint64_t gdim[3] = {(cuuint64_t)(p.dim[2] - m), (cuuint64_t)(p.dim[1] - m), (cuuint64_t)M.G.dim[0] * p.nlevels};
+            cuuint64_t gstride[2] = {(cuuint64_t)M.G.s[1] * 4, (cuuint64_t)M.G.s[0] * 4};
+            cuuint32_t box[3] = {(cuuint32_t)FusedCfg<2>::EZ, (cuuint32_t)FusedCfg<2>::PCY, 1};
+            cuuint32_t estr[3] = {1, 1, 1};
+            ok = encode(&R.smaps_pair.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, R.dev[ring_field[k]], gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        if (!ok) return fail("cuTensorMapEncodeTiled failed (pair store maps)");
+        CUDA_OK(cudaFuncSetAttribute(fused_step<4, OPESCI_ARITH_REFERENCE, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<2>::PSMEM));
+        CUDA_OK(cudaFuncSetAttribute(fused_step<4, OPESCI_ARITH_FAST, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<2>::PSMEM));
+        R.pair = true;
     }
     R.fused = true;
     return 0;

@@ -8,7 +8,7 @@ import __graft_entry__ as ge
 lib = abi.load_library()
 ora = abi.bind(ctypes.CDLL(ge.build_oracle()))
 for steps in (1, 2):
-    cfg = dict(kind="eigenwave3d", so=4, grid_size=[40, 36, 70], dt=0.002, steps=steps, double=False, domain=[1.0, 0.9, 0.8], rho=1.2, vp=1.6, vs=0.8)
+    cfg = dict(kind="eigenwave3d", so=4, grid_size=[40, 60, 130], dt=0.002, steps=steps, double=False, domain=[1.0, 0.9, 0.8], rho=1.2, vp=1.6, vs=0.8)
     a = make_grid(cfg, flags=abi.ARITH_REFERENCE | abi.HOST_MIRROR_FULL); a.run(library=lib)
     b = make_grid(cfg); b.run(library=ora)
     fa, fb = fields_of(a), fields_of(b)

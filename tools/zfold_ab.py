@@ -8,7 +8,7 @@ n = int(os.environ.get("AB_N", "1024"))
 steps = int(os.environ.get("AB_STEPS", "12"))
 lib = abi.load_library()
 for rep in range(2):
-    for extra, tag in ((0, "zfold"), (abi.NO_ZFOLD, "no-zfold")):
+    for extra, tag in ((0, "pair"), (abi.NO_PAIR, "zfold"), (abi.NO_ZFOLD, "no-zfold")):
         for arith, nm in ((abi.ARITH_FAST, "fast"), (abi.ARITH_REFERENCE, "ref")):
             cfg = dict(kind="eigenwave3d", so=4, grid_size=[n, n, n], dt=0.25 / n, steps=steps, double=False, domain=[1.0, 1.0, 1.0])
             g = make_grid(cfg, flags=arith | abi.HOST_MIRROR_NONE | extra)
