@@ -313,7 +313,7 @@ fused_step(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     constexpr int RD = K::RD;
     constexpr int VT = K::VTILE / 4;      // floats per velocity tile
     constexpr int ST = (PAIR ? K::PSTILE : K::STILE) / 4;      // floats per stress tile
-    static_assert(!PAIR || (!ZF && !HET), "pairs: interior launch of the homogeneous model only");
+    static_assert(!PAIR || !ZF, "pairs: not for the z-edge variant");
     // dynamic shared memory (no static __shared__ in this kernel, so the window starts 1024-B
     // aligned): [3][RD] velocity tiles | [5][SR] stress tiles | mbarriers
     extern __shared__ __align__(1024) unsigned char smem[];

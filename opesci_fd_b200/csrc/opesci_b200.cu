@@ -989,7 +989,7 @@ struct Stepper {
             } else
 #endif
 #if OPESCI_TMA_STORE
-            if (Md.p.hetero) fused_step<SO, ARITH, true><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A, R.smaps);
+            if (Md.p.hetero && !(SO == 4 && R.pair)) fused_step<SO, ARITH, true><<<grid, K::THREADS, K::SMEM, st>>>(R.tmap[0], R.tmap[1], R.tmap[2], A, R.smaps);
             else if (SO == 4 && R.pair) {
                 if constexpr (SO == 4) {
                     // 2-CTA clusters stacked in y: a pair stores 2 * PCY rows
@@ -1000,7 +1000,8 @@ struct Stepper {
                     at[0].id = cudaLaunchAttributeClusterDimension;
                     at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
                     cfg.attrs = at; cfg.numAttrs = 1;
-                    cudaError_t e = cudaLaunchKernelEx(&cfg, fused_step<SO, ARITH, false, false, true>, R.tmap[0], R.tmap[1], R.tmap[2], A, R.smaps_pair);
+                    cudaError_t e = Md.p.hetero ? cudaLaunchKernelEx(&cfg, fused_step<SO, ARITH, true, false, true>, R.tmap[0], R.tmap[1], R.tmap[2], A, R.smaps_pair)
+                                                : cudaLaunchKernelEx(&cfg, fused_step<SO, ARITH, false, false, true>, R.tmap[0], R.tmap[1], R.tmap[2], A, R.smaps_pair);
                     if (e != cudaSuccess && err == cudaSuccess) err = e;
                 }
             }
@@ -1327,7 +1328,8 @@ int setup_fused(Run &R)
     }
     // ---- pairs: the interior launch of the z-fold configuration as 2-CTA clusters stacked in y (fused.cuh, PAIR)
     R.pair = false;
-    if (R.zfold && !(p.flags & OPESCI_NO_PAIR) && !getenv("OPESCI_NO_PAIR") && nztiles >= 3) {
+    // (homogeneous: the interior columns beside the z-edge launch; heterogeneous: every column)
+    if (m == 2 && (p.hetero || (R.zfold && nztiles >= 3)) && !(p.flags & OPESCI_NO_PAIR) && !getenv("OPESCI_NO_PAIR") && p.dim[1] >= 4 * m + 6) {
         const int ring_field[5] = {F_TXY, F_TXZ, F_TYY, F_TYZ, F_TZZ};
         bool ok = true;
         for (int k = 0; k < 5 && ok; ++k) {
@@ -1342,6 +1344,8 @@ int setup_fused(Run &R)
         if (!ok) return fail("cuTensorMapEncodeTiled failed (pair store maps)");
         CUDA_OK(cudaFuncSetAttribute(fused_step<4, OPESCI_ARITH_REFERENCE, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<2>::PSMEM));
         CUDA_OK(cudaFuncSetAttribute(fused_step<4, OPESCI_ARITH_FAST, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<2>::PSMEM));
+        CUDA_OK(cudaFuncSetAttribute(fused_step<4, OPESCI_ARITH_REFERENCE, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<2>::PSMEM));
+        CUDA_OK(cudaFuncSetAttribute(fused_step<4, OPESCI_ARITH_FAST, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<2>::PSMEM));
         R.pair = true;
     }
     R.fused = true;
