@@ -104,3 +104,22 @@ def test_free_surface_on_a_subset_of_the_faces(so, size, faces, double, cuda_lib
         c.free()
     a.free()
     b.free()
+
+
+@pytest.mark.parametrize("arith", [abi.ARITH_REFERENCE, abi.ARITH_FAST])
+@pytest.mark.parametrize("kind", ["eigenwave3d", "eigenwave3d_read"])
+def test_fused_path_variants_are_bit_identical(kind, arith, cuda_lib):
+    """The shipped schedule (z-face loops in the z-edge tiles, interior tiles as y-stacked 2-CTA clusters exchanging their
+    inner halo rows through distributed shared memory) against the same kernel without clusters (NO_PAIR) and with the
+    z-face loops back in the separate face kernels (NO_ZFOLD): every cell of every field on both levels identical, in both
+    arithmetic modes -- the variants change where bytes travel, never an operand or an operation."""
+    cfg = dict(kind=kind, so=4, grid_size=[70, 95, 190], dt=0.0015, steps=11, double=False,
+               domain=[1.0, 0.9, 1.2], rho=1.1, vp=1.9, vs=1.0, seed=11)
+    out = []
+    for extra in (0, abi.NO_PAIR, abi.NO_PAIR | abi.NO_ZFOLD):
+        g = make_grid(cfg, flags=arith | abi.HOST_MIRROR_FULL | extra)
+        g.run(library=cuda_lib)
+        out.append(fields_of(g))
+        g.free()
+    assert int((bits(out[0]) != bits(out[1])).sum()) == 0
+    assert int((bits(out[0]) != bits(out[2])).sum()) == 0
