@@ -421,6 +421,7 @@ def main():
     sampler.stop_flag = True
     sampler.join()
     loop_s, pts, launches = timing(lib)
+    halo_transport = abi.HALO_TRANSPORTS.get(lib.opesci_b200_halo_transport(), "?") if world > 1 else None
     if world > 1:
         t = torch.tensor([loop_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -559,8 +560,8 @@ def main():
                 "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64" if C["double"] else "f32", "data": "synthetic",
                 "config": {"workload": "%s, %s" % (C["what"], dims_txt)
-                                       + (", %d^3 per GPU as x-slabs with 8 halo planes exchanged by NCCL send/recv (overlapped with "
-                                          "the next step)" % n if world > 1 else ""),
+                                       + (", %d^3 per GPU as x-slabs with 8 halo planes refreshed after the stress / the velocity ghost loops "
+                                          "(transport: see halo_transport)" % n if world > 1 else ""),
                            "name": args.config,
                            "arithmetic": args.arith,
                            "l2_flush": "no explicit flush: working set %.1f GB per GPU >> 126 MB L2"
@@ -571,6 +572,8 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu}
         if slab_parity is not None:
             line["slab_parity"] = slab_parity
+        if halo_transport is not None:
+            line["config"]["halo_transport"] = halo_transport
         if C["kind"] == "eigenwave3d_read":
             line["config"]["media_generation_s"] = media_gen_s
         print(json.dumps(line))

@@ -269,13 +269,18 @@ int opesci_b200_release_host(void);
 /* ---- multi-GPU: x-slab decomposition (no reference counterpart: the reference is OpenMP only) ----
  * One process per GPU.  dim1 is split into contiguous slabs; every rank keeps OPESCI_SLAB_HALO planes
  * of all fields on each inner side, computes a whole time step on its local slab (x-face loops only
- * on the first / last rank) and then refreshes the halo planes by NCCL send/recv.  The host
- * distributes the 128-byte NCCL unique id (rank 0 creates it), e.g. with torch.distributed. */
+ * on the first / last rank) and then refreshes the halo planes from its neighbours.  Transport: by default every
+ * rank maps its neighbours' field allocations (cudaIpc) and its copy engines pull the planes over NVLink, NCCL
+ * carrying one 4-byte token per neighbour and exchange for the ordering; OPESCI_HALO_P2P=0 in the environment, or
+ * a platform where the mapping fails, moves the planes with ncclSend/ncclRecv instead (same planes, same results).
+ * The host distributes the 128-byte NCCL unique id (rank 0 creates it), e.g. with torch.distributed. */
 #define OPESCI_SLAB_HALO 8       /* minimum halo; the halo is max(8, need) with `need` from include/opesci_slab.h: 8 planes up to so=8, 2m beyond */
 #define OPESCI_COMM_ID_BYTES 128
 int opesci_b200_comm_unique_id(void *out_id, int nbytes);
 int opesci_b200_comm_init(int rank, int nranks, const void *id, int nbytes);
 int opesci_b200_comm_finalize(void);
+/* halo transport of this thread's last opesci_execute: 0 no slabs, 1 ncclSend/Recv, 2 peer memory, 3 loopback copies */
+int opesci_b200_halo_transport(void);
 /* the planes [L0,L1) of global dim1 that rank `rank` of `nranks` stores (its slab plus halos): what a
  * heterogeneous run has to supply in rho/vp/vs (media_plane0 = L0, media_nplanes = L1-L0); staggered elastic model */
 int opesci_b200_slab_range(int rank, int nranks, int gdim1, int so, int *L0, int *L1);

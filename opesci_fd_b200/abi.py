@@ -109,7 +109,7 @@ EXPORTED_SYMBOLS = [
     "opesci_b200_is_cuda", "opesci_b200_time_kernels",
     "opesci_b200_comm_unique_id", "opesci_b200_comm_init", "opesci_b200_comm_finalize",
     "opesci_b200_reserve_host", "opesci_b200_release_host", "opesci_b200_slab_range",
-    "opesci_b200_execute_loopback", "opesci_b200_time_fused_parts",
+    "opesci_b200_execute_loopback", "opesci_b200_time_fused_parts", "opesci_b200_halo_transport",
 ]
 # include/opesci_io.h (model input / field output around the path)
 IO_SYMBOLS = [
@@ -121,6 +121,7 @@ IO_SYMBOLS = [
 ]
 SLAB_HALO = 8
 COMM_ID_BYTES = 128
+HALO_TRANSPORTS = {0: "none", 1: "nccl send/recv", 2: "peer memory (cudaIpc mapping, copy-engine pulls, NCCL tokens)", 3: "loopback copies"}
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CUDA_LIBRARY = os.path.join(_PKG_DIR, "csrc", "libopesci_b200.so")
@@ -148,6 +149,9 @@ def bind(lib):
     if hasattr(lib, "opesci_b200_time_fused_parts"):
         lib.opesci_b200_time_fused_parts.argtypes = [POINTER(OpesciGrid), ctypes.c_int, POINTER(c_double)]
         lib.opesci_b200_time_fused_parts.restype = ctypes.c_int
+    if hasattr(lib, "opesci_b200_halo_transport"):
+        lib.opesci_b200_halo_transport.argtypes = []
+        lib.opesci_b200_halo_transport.restype = ctypes.c_int
     if hasattr(lib, "opesci_b200_reserve_host"):
         lib.opesci_b200_reserve_host.argtypes = [ctypes.c_size_t, ctypes.c_int]
         lib.opesci_b200_reserve_host.restype = ctypes.c_int

@@ -108,6 +108,10 @@ int nccl_bind()
     } while (0)
 
 
+// halo transport of the last run of this thread (opesci_b200_halo_transport): 0 none, 1 NCCL send/recv,
+// 2 peer memory (neighbour's fields mapped with cudaIpc, planes pulled by the copy engines), 3 loopback copies
+thread_local int tl_halo_transport = 0;
+
 // ------------------------------------------------------------------ loopback slabs
 // N logical ranks of one model executed concurrently on ONE device, each by its own host thread running the very same
 // run_model schedule a real rank runs (chunk table, ev_fork / ev_join, exchange on its own stream); only the transport of
@@ -192,6 +196,7 @@ struct Run {
     int nchunks = 1;                // x-chunks of the fused kernel: chunk c covers planes [xs[c], xs[c+1])
     int xs[OPESCI_MAX_CHUNKS + 1] = {};
     int zstrip = 0;                 // > 0: the fused kernel covers z < zstrip only; the thin strip [zstrip, dim-m) is done per point
+    bool split_exchange = false;    // slabs: stress / velocity halo exchanges issued separately (setup_fused)
     int mid0 = 0, mid1 = 0;         // slabs: chunks [mid0, mid1) read no halo plane (they overlap the halo exchange)
     opesci_generic::Module gen;     // OPESCI_KIND_REGULAR_GENERIC: the NVRTC-compiled kernels of this model
     bool pair = false;              // interior fused launch as 2-CTA clusters stacked in y (fused.cuh, PAIR)
@@ -461,11 +466,51 @@ int sm_count()
 #ifndef OPESCI_ZF_SUB
 #define OPESCI_ZF_SUB 8   /* x-chunks of the z-edge launch per x-chunk of the interior launch (B200, 1024^3: 1 -> 22.19, 3 -> 21.83, 8 -> 21.63 ms per step) */
 #endif
+// Diagnostic (OPESCI_STEP_TRACE=1): CUDA events at the phase boundaries of every timed step of the staggered loop, the
+// average time of each phase printed to stderr after the run.  Not part of any measured number: it disables the graph.
+struct PhaseTrace {
+    static const int NPH = 6;   // step start | fused | stress ghost loops | velocity shell | velocity ghost loops | halo wait
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    void mark(cudaStream_t st)
+    {
+        if (!on || ev.size() >= (size_t)NPH * 256) return;
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+    }
+    void reset() { for (cudaEvent_t e : ev) cudaEventDestroy(e); ev.clear(); }
+    void report(int rank)
+    {
+        const size_t nst = ev.size() / NPH;
+        if (on && nst > 0) {
+            static const char *names[NPH] = {"", "fused", "stress_bc", "velocity_shell", "velocity_bc", "halo_wait"};
+            double sum[NPH] = {0, 0, 0, 0, 0, 0}, gap = 0.0;
+            for (size_t k = 0; k < nst; ++k) {
+                for (int ph = 1; ph < NPH; ++ph) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, ev[k * NPH + ph - 1], ev[k * NPH + ph]);
+                    sum[ph] += ms;
+                }
+                if (k + 1 < nst) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[k * NPH + NPH - 1], ev[(k + 1) * NPH]); gap += ms; }
+            }
+            fprintf(stderr, "[opesci trace] rank %d, %zu steps, ms per step:", rank, nst);
+            for (int ph = 1; ph < NPH; ++ph) fprintf(stderr, " %s %.3f", names[ph], sum[ph] / nst);
+            fprintf(stderr, " between_steps %.3f\n", nst > 1 ? gap / (nst - 1) : 0.0);
+        }
+        reset();
+    }
+    ~PhaseTrace() { reset(); }
+};
+
 struct Stepper {
     const Run &R;
     cudaStream_t st;
     long long launches = 0;
     cudaError_t err = cudaSuccess;
+    PhaseTrace *trace = nullptr;
+    void mark() { if (trace) trace->mark(st); }
     Stepper(const Run &r, cudaStream_t s) : R(r), st(s) {}
 
     FieldPtrs ptrs() const
@@ -1099,10 +1144,15 @@ struct Stepper {
     {
         const int t0 = ti % 2, t1 = (t0 + 1) % 2;   // opesci/regulargrid.py:408-433
         if (R.fused) {
+            mark();
             fused<SO, T, ARITH>(t0, t1);             // stress everywhere + velocity of the deep interior
+            mark();
             stress_bc<T>(t0, t1, false);
+            mark();
             velocity_shell<SO, T, ARITH>(t0, t1);    // velocity next to the faces, after the stress ghost loops
+            mark();
             velocity_bc<T>(t1);
+            mark(); mark();
         } else {
             stress<SO, T, ARITH>(t0, t1);
             stress_bc<T>(t0, t1, false);
@@ -1282,7 +1332,13 @@ int setup_fused(Run &R)
     };
     uniform(m, M.G.dim[0] - m, R.nchunks, 0);
     R.mid0 = 0; R.mid1 = 0;
-    if (M.slab.nranks > 1) {
+    // Slabs, default schedule (run_model): the stress fields are exchanged right after the stress ghost loops and the
+    // velocities after the velocity ghost loops, so ONE fused launch covers the whole slab.  The older schedule (the full
+    // exchange overlapped with the middle chunks of the next step, thin end chunks behind it) is kept for runs with point
+    // sources -- they write stress after the stress ghost loops -- and for A/B (OPESCI_SLAB_MIDOVERLAP=1).
+    R.split_exchange = M.slab.nranks > 1 && !(p.n_receivers > 0 || p.src_nt > 0) &&
+                       !(getenv("OPESCI_SLAB_MIDOVERLAP") && atoi(getenv("OPESCI_SLAB_MIDOVERLAP")) != 0);
+    if (M.slab.nranks > 1 && !R.split_exchange) {
         // Slabs: the fused kernel at plane x reads planes x-2m .. x+2m-1 (+1).  Thin end chunks hold every plane whose
         // computation reads a halo plane; the chunks in between can run while the halo exchange of the previous step
         // is still in flight (run_model).
@@ -1385,9 +1441,107 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
         S.template acoustic<SO, T, ARITH>(0, 0, 1, true);   // second initialisation: level 1 from level 0
     }
     const bool slabs = M.slab.nranks > 1;
-    // halo refresh: all fields, one time level, H planes per inner side (contiguous blocks)
-    auto exchange = [&](int level, cudaStream_t xs_) -> int {
+    // ---- peer-memory halo transport (one process per GPU over NCCL): every rank exports its field allocations with
+    // cudaIpcGetMemHandle, maps its neighbours' and PULLS their owned planes into its halo planes with plain device
+    // copies -- the copy engines move them over NVLink at link rate and no SM is taken from the kernels running beside
+    // the transfer (ncclSend/Recv of the same planes reached ~180 GB/s per direction next to the fused kernel).  NCCL
+    // only carries a 4-byte token per neighbour and exchange: my receive completing means the neighbour's stream has
+    // reached the same exchange, i.e. its planes of this level are final; and because a rank enters exchange k+1 only
+    // after its pulls of exchange k have completed (stream order), the same token releases the planes read in exchange
+    // k for overwriting.  OPESCI_HALO_P2P=0 keeps ncclSend/Recv for the planes themselves.
+    struct PeerHalo {
+        bool on = false;
+        void *peer[2][OPESCI_MAX_FIELDS];      // [side][field]: the neighbour's allocation, mapped into this process
+        long long level[2] = {0, 0};           // the neighbour's level stride (elements)
+        int L0[2] = {0, 0};                    // first plane the neighbour stores
+        int *d_tok = nullptr;                  // tokens: [0,1] sent to lo / hi, [2,3] received
+        PeerHalo() { for (auto &sd : peer) for (void *&q : sd) q = nullptr; }
+        void close()
+        {
+            for (auto &sd : peer)
+                for (void *&q : sd)
+                    if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+            on = false;
+        }
+        ~PeerHalo() { close(); if (d_tok) cudaFree(d_tok); }
+    } PH;
+    auto tokens = [&](cudaStream_t xs_) -> int {
+        const OpesciSlab &sl = M.slab;
+        NCCL_OK(g_nccl.GroupStart());
+        if (!sl.lo_face) {
+            NCCL_OK(g_nccl.Send(PH.d_tok + 0, sizeof(int), ncclUint8, sl.rank - 1, g_nccl.comm, xs_));
+            NCCL_OK(g_nccl.Recv(PH.d_tok + 2, sizeof(int), ncclUint8, sl.rank - 1, g_nccl.comm, xs_));
+        }
+        if (!sl.hi_face) {
+            NCCL_OK(g_nccl.Send(PH.d_tok + 1, sizeof(int), ncclUint8, sl.rank + 1, g_nccl.comm, xs_));
+            NCCL_OK(g_nccl.Recv(PH.d_tok + 3, sizeof(int), ncclUint8, sl.rank + 1, g_nccl.comm, xs_));
+        }
+        NCCL_OK(g_nccl.GroupEnd());
+        return 0;
+    };
+    tl_halo_transport = !slabs ? 0 : tl_loop ? 3 : 1;
+    if (slabs && !tl_loop && !(getenv("OPESCI_HALO_P2P") && atoi(getenv("OPESCI_HALO_P2P")) == 0)) {
+        struct Pack { cudaIpcMemHandle_t h[OPESCI_MAX_FIELDS]; int ok; };
+        const OpesciSlab &sl = M.slab;
+        Pack mine, theirs[2];
+        memset(&mine, 0, sizeof mine);
+        memset(theirs, 0, sizeof theirs);
+        mine.ok = 1;
+        for (int f = 0; f < p.nfields; ++f)
+            if (cudaIpcGetMemHandle(&mine.h[f], R.dev[f]) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+        Pack *d_pack = nullptr;
+        double *d_bad = nullptr;
+        CUDA_OK(cudaMalloc(&d_pack, 3 * sizeof(Pack)));
+        CUDA_OK(cudaMalloc(&d_bad, sizeof(double)));
+        CUDA_OK(cudaMalloc(&PH.d_tok, 4 * sizeof(int)));
+        CUDA_OK(cudaMemsetAsync(PH.d_tok, 0, 4 * sizeof(int), st));
+        CUDA_OK(cudaMemcpyAsync(d_pack, &mine, sizeof(Pack), cudaMemcpyHostToDevice, st));
+        NCCL_OK(g_nccl.GroupStart());
+        if (!sl.lo_face) {
+            NCCL_OK(g_nccl.Send(d_pack, sizeof(Pack), ncclUint8, sl.rank - 1, g_nccl.comm, st));
+            NCCL_OK(g_nccl.Recv(d_pack + 1, sizeof(Pack), ncclUint8, sl.rank - 1, g_nccl.comm, st));
+        }
+        if (!sl.hi_face) {
+            NCCL_OK(g_nccl.Send(d_pack, sizeof(Pack), ncclUint8, sl.rank + 1, g_nccl.comm, st));
+            NCCL_OK(g_nccl.Recv(d_pack + 2, sizeof(Pack), ncclUint8, sl.rank + 1, g_nccl.comm, st));
+        }
+        NCCL_OK(g_nccl.GroupEnd());
+        CUDA_OK(cudaMemcpyAsync(theirs, d_pack + 1, 2 * sizeof(Pack), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        double bad = mine.ok ? 0.0 : 1.0;
+        const char *why = mine.ok ? "" : "cudaIpcGetMemHandle failed";
+        for (int side = 0; side < 2 && bad == 0.0; ++side) {
+            if (side == 0 ? sl.lo_face : sl.hi_face) continue;
+            if (!theirs[side].ok) { bad = 1.0; why = "a neighbour could not export its fields"; break; }
+            OpesciSlab ns;
+            opesci_slab_make(&ns, sl.rank + (side == 0 ? -1 : 1), sl.nranks, sl.gdim, M.m, OPESCI_SLAB_HALO, sl.halo);
+            PH.L0[side] = ns.L0;
+            PH.level[side] = (long long)(ns.L1 - ns.L0) * M.G.s[0];
+            for (int f = 0; f < p.nfields; ++f)
+                if (cudaIpcOpenMemHandle(&PH.peer[side][f], theirs[side].h[f], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    PH.peer[side][f] = nullptr; cudaGetLastError(); bad = 1.0; why = "cudaIpcOpenMemHandle failed"; break;
+                }
+        }
+        // all ranks use the same transport: the sum of the failure flags decides
+        const double my_bad = bad;
+        CUDA_OK(cudaMemcpyAsync(d_bad, &bad, sizeof(double), cudaMemcpyHostToDevice, st));
+        NCCL_OK(g_nccl.AllReduce(d_bad, d_bad, 1, ncclFloat64, ncclSum, g_nccl.comm, st));
+        CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        cudaFree(d_pack);
+        cudaFree(d_bad);
+        if (bad == 0.0) { PH.on = true; tl_halo_transport = 2; }
+        else {
+            PH.close();
+            if (my_bad != 0.0 || sl.rank == 0)
+                fprintf(stderr, "[opesci_b200] rank %d: peer-memory halo transport not available (%s); the planes travel by ncclSend/Recv\n",
+                        sl.rank, my_bad != 0.0 ? why : "another rank could not map its neighbour");
+        }
+    }
+    // halo refresh: fields [f0, f1), one time level, H planes per inner side (contiguous blocks)
+    auto exchange = [&](int level, cudaStream_t xs_, int f0 = 0, int f1 = -1) -> int {
         cudaStream_t st = xs_;
+        if (f1 < 0) f1 = p.nfields;
         const OpesciSlab &sl = M.slab;
         const size_t plane = (size_t)M.G.s[0], nel = (size_t)sl.halo * plane;
         if (tl_loop) {
@@ -1402,7 +1556,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
                 const Run &N = *L.runs[nb];
                 const OpesciSlab &ns = N.M.slab;
                 CUDA_OK(cudaStreamWaitEvent(st, L.done[nb], 0));
-                for (int f = 0; f < p.nfields; ++f) {
+                for (int f = f0; f < f1; ++f) {
                     T *mine = (T *)R.dev[f] + (size_t)level * M.G.level;
                     const T *theirs = (const T *)N.dev[f] + (size_t)level * N.M.G.level;
                     // low halo [X0-halo, X0) = the neighbour's last owned planes; high halo [X1, X1+halo) = its first ones
@@ -1417,8 +1571,23 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
                 if (nb >= 0 && nb < L.nranks) CUDA_OK(cudaStreamWaitEvent(st, L.xdone[nb], 0));
             return 0;
         }
+        if (PH.on) {
+            if (tokens(st)) return 1;
+            for (int side = 0; side < 2; ++side) {
+                if (side == 0 ? sl.lo_face : sl.hi_face) continue;
+                // low halo [X0-halo, X0) = the neighbour's last owned planes; high halo [X1, X1+halo) = its first ones
+                const size_t dst = side == 0 ? 0 : (size_t)(sl.X1 - sl.L0);
+                const size_t src = side == 0 ? (size_t)(sl.X0 - sl.halo - PH.L0[0]) : (size_t)(sl.X1 - PH.L0[1]);
+                for (int f = f0; f < f1; ++f) {
+                    T *mine = (T *)R.dev[f] + (size_t)level * M.G.level;
+                    const T *theirs = (const T *)PH.peer[side][f] + (size_t)level * PH.level[side];
+                    CUDA_OK(cudaMemcpyAsync(mine + dst * plane, theirs + src * plane, nel * sizeof(T), cudaMemcpyDefault, st));
+                }
+            }
+            return 0;
+        }
         NCCL_OK(g_nccl.GroupStart());
-        for (int f = 0; f < p.nfields; ++f) {
+        for (int f = f0; f < f1; ++f) {
             T *base = (T *)R.dev[f] + (size_t)level * M.G.level;
             if (!sl.lo_face) {
                 NCCL_OK(g_nccl.Send(base + (size_t)(sl.X0 - sl.L0) * plane, nel * sizeof(T), ncclUint8, sl.rank - 1, g_nccl.comm, st));
@@ -1472,6 +1641,8 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     cudaEvent_t &e0 = H.e0, &e1 = H.e1;
     CUDA_OK(cudaEventCreate(&e0));
     CUDA_OK(cudaEventCreate(&e1));
+    PhaseTrace trace;
+    trace.on = staggered && getenv("OPESCI_STEP_TRACE") && atoi(getenv("OPESCI_STEP_TRACE")) != 0;
     const int nsteps = p.ntsteps;
     int warm = p.warmup_steps > 0 ? p.warmup_steps : 0;   // the first `warmup_steps` steps run untimed (bench contract)
     if (warm > nsteps) warm = nsteps;
@@ -1480,7 +1651,83 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
     cudaGraphExec_t &gexec = H.gexec;
     cudaStream_t &st2 = H.st2;
     cudaEvent_t &ev_fork = H.ev_fork, &ev_join = H.ev_join;
-    if (slabs && staggered && R.fused && R.mid1 > R.mid0) {
+    if (slabs && staggered && R.fused && R.split_exchange) {
+        // ---- slabs, fused kernel, default: one fused launch per step over the whole slab.  The six stress fields of the
+        // new level travel (own high-priority stream) as soon as the stress ghost loops are done, hidden behind the
+        // velocity shell and the velocity ghost loops; the three velocities follow after those -- the only transfer the
+        // next step waits for.  The kernels that run beside the stress transfer read stress halo planes, but every plane
+        // an OWNED cell's computation reads (local index >= m) already holds, bit for bit, what the neighbour sends
+        // (include/opesci_slab.h), and the velocity they leave on the halo planes is replaced by the second transfer.
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_OK(cudaStreamCreateWithPriority(&st2, cudaStreamNonBlocking, prio_hi));
+        CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));   // work on st done -> transfer may start
+        CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));   // both transfers done -> halo planes valid
+        auto step = [&](int ti) -> int {
+            const int t0 = ti % 2, t1 = (t0 + 1) % 2;
+            S.mark();
+            SNAP_OK(snap.before_step(st, ti));
+            S.template fused<SO, T, ARITH>(t0, t1);
+            S.mark();
+            S.template stress_bc<T>(t0, t1, false);
+            S.mark();
+            CUDA_OK(cudaEventRecord(ev_fork, st));
+            CUDA_OK(cudaStreamWaitEvent(st2, ev_fork, 0));
+            if (exchange(t1, st2, F_TXX, p.nfields)) return 1;
+            S.template velocity_shell<SO, T, ARITH>(t0, t1);
+            S.mark();
+            S.template velocity_bc<T>(t1);
+            S.mark();
+            SNAP_OK(snap.after_step(st, ti, t1));   // owned planes only: they are final before the halo exchange
+            CUDA_OK(cudaEventRecord(ev_fork, st));
+            CUDA_OK(cudaStreamWaitEvent(st2, ev_fork, 0));
+            if (exchange(t1, st2, F_U, F_TXX)) return 1;
+            CUDA_OK(cudaEventRecord(ev_join, st2));
+            CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));   // the next step starts with valid halo planes
+            S.mark();
+            return 0;
+        };
+        // Two steps (the time-level indices repeat with period 2) are captured into one CUDA graph and replayed, like the
+        // single-GPU loop: both streams, the token kernels and the peer copies (or the ncclSend/Recv pairs) become nodes
+        // of it -- measured on one GPU the replayed graph saves 0.56 ms of a 21.1 ms step.  Not with loopback ranks
+        // (host barriers inside the exchange), per-step output or the phase trace.
+        const bool slab_graph = !tl_loop && !(p.flags & OPESCI_NO_CUDA_GRAPH) && !getenv("OPESCI_NO_CUDA_GRAPH") && !snap.armed && !trace.on &&
+                                nsteps - warm >= 2 * period;
+        int ti = 0;
+        for (; ti < warm; ++ti)
+            if (step(ti)) return 1;
+        int graph_parity = 0;
+        if (slab_graph) {
+            // (NCCL's connections to both neighbours exist already: the exchange after the initialisation made them)
+            CUDA_OK(cudaStreamSynchronize(st));
+            graph_parity = ti % 2;
+            const long long before = S.launches;
+            CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            H.cap = st;
+            if (step(ti) || step(ti + 1)) return 1;
+            per_period = S.launches - before;
+            H.cap = nullptr;
+            CUDA_OK(cudaStreamEndCapture(st, &graph));
+            CUDA_OK(cudaGraphInstantiate(&gexec, graph, 0));
+            S.launches = before;
+        }
+        if (warm > 0) S.launches = 0;
+        if (trace.on) S.trace = &trace;
+        CUDA_OK(cudaEventRecord(e0, st));
+        while (ti < nsteps) {
+            if (gexec && ti % 2 == graph_parity && ti + 2 <= nsteps) {
+                CUDA_OK(cudaGraphLaunch(gexec, st));
+                S.launches += per_period;
+                ti += 2;
+            } else {
+                if (step(ti)) return 1;
+                ++ti;
+            }
+        }
+        CUDA_OK(cudaEventRecord(e1, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        CUDA_OK(cudaStreamSynchronize(st2));
+    } else if (slabs && staggered && R.fused && R.mid1 > R.mid0) {
         // ---- slabs, fused kernel: the halo exchange of step n (NCCL, own high-priority stream) runs while the middle
         // x-chunks of step n+1 -- which read no halo plane -- are computed; the thin end chunks, the ghost loops and
         // the shell follow once the exchange has landed.  Same kernels, same per-cell order as the serial schedule.
@@ -1525,7 +1772,7 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
         CUDA_OK(cudaStreamSynchronize(st));
         CUDA_OK(cudaStreamSynchronize(st2));
     } else {
-    const bool use_graph = !(p.flags & OPESCI_NO_CUDA_GRAPH) && nsteps >= 2 * period && !slabs && !snap.armed;
+    const bool use_graph = !(p.flags & OPESCI_NO_CUDA_GRAPH) && !getenv("OPESCI_NO_CUDA_GRAPH") && nsteps >= 2 * period && !slabs && !snap.armed && !trace.on;
     if (use_graph) {
         // one period of steps (time-level indices repeat with it) captured once, replayed
         CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -1564,11 +1811,22 @@ template <int SO, typename T, int ARITH> int run_model(Run &R, cudaStream_t st, 
         if (run_steps(warm)) return 1;
         S.launches = 0;
     }
+    if (trace.on) S.trace = &trace;
     CUDA_OK(cudaEventRecord(e0, st));
     if (run_steps(nsteps)) return 1;
     CUDA_OK(cudaEventRecord(e1, st));
     }
     CUDA_OK(cudaStreamSynchronize(st));
+    if (PH.on) {
+        // my pulls are complete (both streams were synchronised): unmap the neighbours' fields, then meet them once more
+        // so that nobody frees an allocation a neighbour still has mapped or is still reading
+        if (st2) CUDA_OK(cudaStreamSynchronize(st2));
+        PH.close();
+        if (tokens(st)) return 1;
+        CUDA_OK(cudaStreamSynchronize(st));
+    }
+    S.trace = nullptr;
+    trace.report(M.slab.rank);
     snap.finish();
     if (opesci_io::write_errors().load() > 0) return fail("per-step field output: writing a .vts file failed");
     if (S.err != cudaSuccess) return fail("kernel launch failed in the time loop: %s", cudaGetErrorString(S.err));
@@ -1961,6 +2219,7 @@ extern "C" {
 
 const char *opesci_b200_last_error(void) { return g_err; }
 int opesci_b200_is_cuda(void) { return 1; }
+int opesci_b200_halo_transport(void) { return tl_halo_transport; }
 
 int opesci_b200_configure(const OpesciB200Params *params)
 {

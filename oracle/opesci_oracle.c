@@ -665,6 +665,7 @@ int opesci_free(OpesciGrid *grid)
 int opesci_b200_comm_unique_id(void *out_id, int nbytes) { (void)out_id; (void)nbytes; return fail("oracle: no NCCL; use opesci_oracle_set_exchange"); }
 int opesci_b200_comm_init(int rank, int nranks, const void *id, int nbytes) { (void)rank; (void)nranks; (void)id; (void)nbytes; return fail("oracle: no NCCL; use opesci_oracle_set_exchange"); }
 int opesci_b200_comm_finalize(void) { return 0; }
+int opesci_b200_halo_transport(void) { return 0; }
 int opesci_b200_slab_range(int rank, int nranks, int gdim1, int so, int *L0, int *L1)
 {
     OpesciSlab sl;

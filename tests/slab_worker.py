@@ -99,6 +99,7 @@ def run_job(outdir, cfg, lib, rank, world, use_cuda):
     if cfg.get("vts_prefix") and use_cuda:
         lib.opesci_b200_set_output(cfg["vts_prefix"].encode(), 0, cfg.get("vts_every", 1))
     grid.run(library=lib)
+    transport = lib.opesci_b200_halo_transport() if use_cuda else 0
     if cfg.get("vts_prefix") and use_cuda:
         lib.opesci_b200_set_output(None, 0, 0)
     p = grid._params
@@ -124,7 +125,7 @@ def run_job(outdir, cfg, lib, rank, world, use_cuda):
     l2 = np.array(grid.convergence_f64())
     rec = grid.receiver_data() if hasattr(grid, 'receiver_data') else None
     np.savez(os.path.join(outdir, "rank%d.npz" % rank), fields=np.stack(fields), L0=L0, L1=L1, own_lo=own_lo, own_hi=own_hi, l2=l2,
-             receivers=rec if rec is not None else np.zeros(0))
+             receivers=rec if rec is not None else np.zeros(0), transport=transport)
     grid.free()
 
 

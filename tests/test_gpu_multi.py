@@ -1,4 +1,6 @@
-"""GPU, 2 ranks over NCCL: the slab-decomposed CUDA run equals the single-GPU run bit for bit."""
+"""GPU, 2 ranks, one process per GPU: the slab-decomposed CUDA run equals the single-GPU run bit for bit -- with the
+default halo transport (the neighbour's fields mapped with cudaIpc, planes pulled by the copy engines, NCCL tokens for
+the ordering) and with the planes sent by ncclSend/ncclRecv (OPESCI_HALO_P2P=0)."""
 import json
 import os
 import socket
@@ -45,7 +47,14 @@ def test_two_gpu_slabs_with_z_strip(kind, cuda_lib, tmp_path):
     _slabs_equal_single(abi.ARITH_REFERENCE, kind, 4, [96, 40, 124], cuda_lib, tmp_path)
 
 
-def _slabs_equal_single(arith, kind, so, size, cuda_lib, tmp_path):
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
+@pytest.mark.parametrize("kind,so", [("eigenwave3d", 4), ("eigenwave3d_read", 4), ("simplewave3d", 4), ("eigenwave3d", 8)])
+def test_two_gpu_slabs_planes_by_nccl_send_recv(kind, so, cuda_lib, tmp_path, monkeypatch):
+    monkeypatch.setenv("OPESCI_HALO_P2P", "0")
+    _slabs_equal_single(abi.ARITH_REFERENCE, kind, so, [96, 70, 130], cuda_lib, tmp_path, transport=1)
+
+
+def _slabs_equal_single(arith, kind, so, size, cuda_lib, tmp_path, transport=2):
     cfg = dict(kind=kind, so=so, grid_size=size, dt=0.002, steps=9, double=False,
                domain=[1.0, 0.9, 0.8], rho=1.2, vp=1.6, vs=0.8, seed=5)
     single = make_grid(cfg, flags=arith | abi.HOST_MIRROR_FULL)
@@ -67,6 +76,7 @@ def _slabs_equal_single(arith, kind, so, size, cuda_lib, tmp_path):
         want = np.ascontiguousarray(ref[:, :, own_lo:own_hi])
         assert int((bits(mine) != bits(want)).sum()) == 0, "rank %d differs from the single-GPU run" % r
         covered += own_hi - own_lo
+        assert int(z["transport"]) == transport, "halo transport %d, expected %d (include/opesci_b200.h)" % (int(z["transport"]), transport)
         # every rank holds the all-reduced global norms
         np.testing.assert_allclose(z["l2"], ref_l2, rtol=1e-12)
     assert covered == ref.shape[2]
