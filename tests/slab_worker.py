@@ -98,6 +98,10 @@ def run_job(outdir, cfg, lib, rank, world, use_cuda):
     grid.build_params = with_slab
     if cfg.get("vts_prefix") and use_cuda:
         lib.opesci_b200_set_output(cfg["vts_prefix"].encode(), 0, cfg.get("vts_every", 1))
+    if cfg.get("split_refresh"):
+        os.environ["OPESCI_ORACLE_SPLIT_REFRESH"] = "1"   # oracle: the CUDA slab loop's refresh order
+    else:
+        os.environ.pop("OPESCI_ORACLE_SPLIT_REFRESH", None)
     grid.run(library=lib)
     transport = lib.opesci_b200_halo_transport() if use_cuda else 0
     if cfg.get("vts_prefix") and use_cuda:
