@@ -212,3 +212,40 @@ def test_execute_refuses_a_non_cuda_library(tmp_path):
     g.src_lib = str(tmp_path / "missing.so")
     with pytest.raises(Exception, match="no CPU fallback"):
         g.execute(str(tmp_path / "m.json"))
+
+
+def test_slab_geometry_properties(cuda_lib, oracle_lib):
+    """include/opesci_slab.h through both libraries' `opesci_b200_slab_range` (host arithmetic only, no GPU): for random
+    grids, orders and rank counts the stored ranges are the owned ranges plus exactly max(8, need) halo planes per inner
+    side, the owned ranges tile the grid, and a decomposition is refused exactly when a slab would be thinner than the halo."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(20, 3000), st.sampled_from([2, 4, 6, 8, 10, 12]), st.integers(1, 8))
+    def check(gdim, so, nranks):
+        m = so // 2
+        need = 2 * m + 3 if so == 4 else 2 * m                      # staggered elastic model (opesci_slab_need)
+        halo = max(abi.SLAB_HALO, need)
+        n_int = gdim - 2 * m
+        base, rem = divmod(n_int, nranks)
+        prev_hi = 0
+        for r in range(nranks):
+            got = []
+            for lib in (cuda_lib, oracle_lib):
+                l0, l1 = ctypes.c_int(-1), ctypes.c_int(-1)
+                rc = lib.opesci_b200_slab_range(r, nranks, gdim, so, ctypes.byref(l0), ctypes.byref(l1))
+                got.append((rc != 0, l0.value, l1.value))
+            assert got[0][0] == got[1][0] == (nranks > 1 and base < halo)
+            if got[0][0]:
+                continue
+            assert got[0] == got[1]
+            X0 = m + r * base + min(r, rem)
+            X1 = X0 + base + (1 if r < rem else 0)
+            own_lo, own_hi = (0 if r == 0 else X0), (gdim if r == nranks - 1 else X1)
+            assert own_lo == prev_hi and own_hi > own_lo
+            prev_hi = own_hi
+            assert got[0][1] == (0 if r == 0 else X0 - halo) and got[0][2] == (gdim if r == nranks - 1 else X1 + halo)
+            assert 0 <= got[0][1] and got[0][2] <= gdim
+        if not (nranks > 1 and base < halo):
+            assert prev_hi == gdim
+    check()
